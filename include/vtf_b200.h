@@ -1,0 +1,167 @@
+/*
+ * vtf_b200.h -- C ABI of the B200-native grouping hot path of video-to-faces.
+ *
+ * The reference (sephirot-github/video-to-faces) has no FFI: its grouping stage
+ * (src/videotofaces/dupes.py:51-92, src/videotofaces/grouping.py:50-137) calls scikit-learn,
+ * whose native layer is OpenBLAS SGEMM/DGEMM plus the Cython Lloyd kernels.  Each entry point
+ * below replaces one of those call sites; the citation names the reference line (and the
+ * scikit-learn 1.9.0 routine behind it, "SK/" = site-packages/sklearn) it stands in for.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _h (host);
+ *   - matrices are row-major, C-contiguous; X is [N, d] float32 with d % 4 == 0;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     asynchronous on it and nothing allocates: the caller owns outputs and workspaces;
+ *   - return value: 0 = ok, negative = error (vtf_last_error() gives the text).  There is no
+ *     CPU fallback: without an sm_100 device every compute call fails with VTF_ERR_DEVICE.
+ */
+#ifndef VTF_B200_H
+#define VTF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTF_OK             0
+#define VTF_ERR_ARG       -1
+#define VTF_ERR_CUDA      -2
+#define VTF_ERR_DEVICE    -3
+#define VTF_ERR_WORKSPACE -4
+
+int         vtf_version(void);
+const char* vtf_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t     vtf_launch_count(void);
+/* 0 when the current device is sm_100 (B200); VTF_ERR_DEVICE otherwise. */
+int         vtf_device_check(void);
+
+/* ---- a2: cosine normalisation ------------------------------------------------------------
+ * sklearn.preprocessing.normalize inside cosine_distances (SK/metrics/pairwise.py:1744-1748,
+ * SK/preprocessing/_data.py:2076-2081, zero-norm guard :127-132), called from dupes.py:60 and
+ * grouping.py:51.  fp32 norm, sqrt, divide; norms < 10*eps become 1.                       */
+int vtf_normalize_rows(const float* X, int64_t N, int d, float* Xn, void* stream);
+
+/* ---- a6 prologue: KMeans.fit set-up (SK/cluster/_kmeans.py:1473-1496) -------------------
+ * col_stats: per-column sum and sum of squares in fp64 over the rows given (a rank's shard;
+ * partial results add across ranks).  ws: vtf_col_stats_ws_bytes(d).                      */
+size_t vtf_col_stats_ws_bytes(int d);
+int vtf_col_stats(const float* X, int64_t N, int d, double* col_sum, double* col_sumsq,
+                  void* ws, void* stream);
+/* Xc = X - mean (fp32), SK/cluster/_kmeans.py:1487-1490.                                   */
+int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* Xc, void* stream);
+
+/* ---- a7: k-means++ (SK/cluster/_kmeans.py:180-278) ----------------------------------------
+ * kpp_dist: for T candidate centres cand[T,d], out[t,i] = min(closest[i], ||x_i - cand_t||^2)
+ * with the squared distance computed in fp64 and stored as fp32, clamped at 0
+ * (SK/metrics/pairwise.py:567-638, 413-416); closest == NULL means "no previous centre".
+ * pots[t] = sum_i out[t,i] accumulated in fp64 (:263).  ws: vtf_kpp_ws_bytes(T).           */
+size_t vtf_kpp_ws_bytes(int T);
+int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T,
+                 const float* closest, float* out, double* pots, void* ws, void* stream);
+/* kpp_pick: idx[t] = searchsorted(cumsum_fp32_sequential(closest), thr[t]) clipped to N-1
+ * (:250-254).  thr must be ascending.  `offset_in`/`total_out` chain shards: the running
+ * fp32 sum enters as *offset_in (NULL = 0) and leaves in *total_out (nullable); idx[t] = -1
+ * when thr[t] is not reached inside this shard.                                            */
+int vtf_kpp_pick(const float* closest, int64_t N, const float* thr, int T,
+                 const float* offset_in, float* total_out, int64_t* idx, void* stream);
+
+/* ---- a6: Lloyd iteration (SK/cluster/_k_means_lloyd.pyx:23-218) ---------------------------
+ * assign: labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32, first index on ties (:205-213);
+ * counts[k] += rows per cluster (int64), *n_changed += rows whose label differs from the
+ * previous content of labels[] (strict-convergence test, SK/cluster/_kmeans.py:723).
+ * counts and n_changed are accumulated into (the caller zeroes them).                      */
+int vtf_lloyd_assign(const float* Xc, int64_t N, int d, const float* C, int k,
+                     int32_t* labels, int64_t* counts, int64_t* n_changed, void* stream);
+/* cluster_sums: sums[c,:] = sum of rows with label c, fp64, deterministic (block partials
+ * reduced in a fixed order) -- the M-step accumulation of :215-218 without its thread-order
+ * nondeterminism.  ws: vtf_cluster_sums_ws_bytes(k, d).                                    */
+size_t vtf_cluster_sums_ws_bytes(int k, int d);
+int vtf_cluster_sums(const float* X, int64_t N, int d, const int32_t* labels, int k,
+                     double* sums, void* ws, void* stream);
+/* inertia / dispersion: per cluster c, sq[c] = sum_{i in c} ||x_i - C64[c]||^2 and
+ * rt[c] = sum_{i in c} ||x_i - C64[c]|| (fp64).  sum(sq) is KMeans.inertia_
+ * (SK/cluster/_k_means_common.pyx:94-124) and the intra term of calinski_harabasz_score
+ * (SK/metrics/cluster/_unsupervised.py:394-399); rt/n_c is davies_bouldin's intra_dists
+ * (:467-474).  Also far_d2[i] (nullable) = ||x_i - C[label_i]||^2 fp32 for the
+ * empty-cluster relocation (SK/cluster/_k_means_common.pyx:186).  ws: as cluster_sums.    */
+int vtf_cluster_dispersion(const float* X, int64_t N, int d, const int32_t* labels, int k,
+                           const double* C64, double* sq, double* rt, float* far_d2,
+                           void* ws, void* stream);
+/* M-step finish (SK/cluster/_k_means_common.pyx:274-311): C_new[c] = sums[c]/counts[c] (fp32;
+ * empty clusters take the centre of the biggest one), stats[0] = sum_c |C_new[c]-C_old[c]|^2,
+ * stats[1] = *n_changed, stats[2+c] = counts[c] (doubles: one small D2H per iteration decides
+ * convergence, SK/cluster/_kmeans.py:723-738).  Also writes C64 = double(C_new) when given.  */
+int vtf_lloyd_update(const double* sums, const int64_t* counts, const int64_t* n_changed, int k,
+                     int d, const float* C_old, float* C_new, double* C64, double* stats,
+                     void* stream);
+
+/* ---- a3: nearest-reference classification (grouping.py:51-56) -----------------------------
+ * Xn, Rn are cosine-normalised.  dist[N,R] = clip(1 - Xn.Rn^T, 0, 2) (fp32, kept for the
+ * '%.4f' log, grouping.py:63); label[i] = argmin (first index), or R when
+ * min >= thr (fp32 compare, grouping.py:55); thr < 0 or NaN disables the 'other' class.    */
+int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int R, float thr,
+                        float* dist, int64_t* label, void* stream);
+
+/* ---- a1: all-pairs duplicate marking (dupes.py:60-65) -------------------------------------
+ * Xn cosine-normalised [N,d].  For the row tiles this rank owns (tile t of 64 rows belongs to
+ * rank t % world) computes key[i] = (bits(min_{j<i} D_ij) << 32) | argmin_j with
+ * D = clip(1 - xn_i.xn_j, 0, 2) in fp32 FMA arithmetic; row 0 keeps (bits(10000.f)<<32)|0,
+ * which is what the reference's +10000 mask (dupes.py:62) yields.  key must be pre-filled
+ * with vtf_dedup_init.  min/argmin decode: dist = float(key >> 32), j = key & 0xffffffff.   */
+int vtf_dedup_init(uint64_t* key, int64_t N, void* stream);
+int vtf_cosine_dedup(const float* Xn, int64_t N, int d, int rank, int world,
+                     uint64_t* key, void* stream);
+/* X_out[r,:] = X[idx[r],:]  -- np.delete(X, idx, axis=0) with idx = kept rows (dupes.py:68) */
+int vtf_gather_rows(const float* X, int d, const int64_t* idx, int64_t n_out, float* X_out,
+                    void* stream);
+
+/* ---- a8: silhouette (SK/metrics/cluster/_unsupervised.py:149-200, 211-323) ----------------
+ * Exact path (fp32 FMA Gram, any N; used for small N and as the on-device cross-check):
+ * rowsum[i, c] += sum_{j: label_j == c} sqrt(max(n_i + n_j - 2 x_i.x_j, 0)), D_ii = 0, for
+ * rows i in [row_begin, row_end).  rowsum is fp64 [N, k], zeroed by the caller.            */
+int vtf_silhouette_rowsums_exact(const float* X, const float* sqnorm, int64_t N, int d,
+                                 const int32_t* labels, int k, int64_t row_begin,
+                                 int64_t row_end, double* rowsum, void* stream);
+int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* stream);
+
+/* Tensor-core path (tcgen05 + TMA, the dominant kernel at BASELINE sizes).
+ * Distances do not depend on k, so ONE sweep over the Gram matrix serves every labelling of
+ * the k-range: the caller groups columns by their joint label tuple ("cell"), pads every
+ * cell to a multiple of 32 columns, and the kernel accumulates, for each row, one distance
+ * sum per cell.  See DESIGN.md for the layout.
+ *
+ * pack: Xh[p,:] = fp16(scale * X[perm[p],:]) for p < P (rows with perm[p] < 0 are zero
+ * padding), sqn[p] = |Xh[p,:]|^2 / scale^2 computed from the ROUNDED values (so that the
+ * distance is the exact distance between the rounded points), or -1e30 for padding so the
+ * clamp at 0 removes them.  P % 256 == 0, d % 64 == 0.                                     */
+int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale,
+                 void* Xh, float* sqn, void* stream);
+/* out[0] = max |x| (picks the power-of-two fp16 scale).                                     */
+int vtf_absmax(const float* X, int64_t N, int d, float* out, void* stream);
+/* sweep: cellsum[g, p] += sum_{q in cell g} sqrt(max(sqn[p] + sqn[q] - 2 xh_p.xh_q / scale^2, 0))
+ * for row blocks [rb_begin, rb_end) of 128 rows, D_pp = 0.  chunk_cell[P/32] gives the cell
+ * of every 32-column chunk.  cellsum is fp32 [n_cells, P], zeroed by the caller.
+ * Requires sm_100a; d in {64..1024}, d % 64 == 0.                                          */
+int vtf_sil_sweep(const void* Xh, const float* sqn, int64_t P, int d, float scale,
+                  const int32_t* chunk_cell, int n_cells, int64_t rb_begin, int64_t rb_end,
+                  float* cellsum, void* stream);
+/* finish: for labelling l (k_l clusters), per real row: a = S_own/(n_own-1),
+ * b = min_{c != own} S_c/n_c, s = (b-a)/max(a,b) (0 for singleton clusters, :323), and
+ * out[l] += sum_i s_i in fp64.  From the exact path: vtf_sil_finish_rows on rowsum[N,k].    */
+int vtf_sil_finish_rows(const double* rowsum, int64_t N, int k, const int32_t* labels,
+                        const int64_t* counts, int64_t row_begin, int64_t row_end,
+                        double* out_sum, void* stream);
+/* From the tensor-core path: cellsum[n_cells,P] plus cell_to_cluster[n_cells] for this
+ * labelling; perm[p] < 0 marks padding rows.                                               */
+int vtf_sil_finish_cells(const float* cellsum, int64_t P, int n_cells,
+                         const int32_t* cell_to_cluster, int k, const int64_t* perm,
+                         const int32_t* labels, const int64_t* counts,
+                         int64_t p_begin, int64_t p_end, double* out_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTF_B200_H */

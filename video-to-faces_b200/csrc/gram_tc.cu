@@ -1,0 +1,384 @@
+// Tensor-core silhouette sweep for sm_100a: tcgen05.mma + TMEM accumulators + TMA operand feed.
+//
+// Replaces the dominant cost of the reference path: silhouette_score recomputes all N^2 euclidean
+// distances for every k (grouping.py:104-105 -> SK/metrics/cluster/_unsupervised.py:310 ->
+// SK/metrics/pairwise.py:2279, fp64 DGEMM on 134-row chunks) and reduces them with a Python loop of
+// np.bincount (_unsupervised.py:184-189).  Here ONE pass over the Gram matrix X.X^T serves every
+// labelling of the k-range.
+//
+// Layout (DESIGN.md "silhouette sweep"):
+//   Xh   [P, d] fp16, rows permuted so that every 32-column chunk belongs to one "cell" (= one joint
+//        label tuple over all labellings), zero rows as padding, values scaled by a power of two.
+//   sqn  [P]    fp32 squared norms of the rounded rows (padding: -1e30 so the clamp removes it).
+//   cellsum [n_cells, P] fp32: sum over the columns of a cell of sqrt(max(n_p + n_q - 2 x_p.x_q, 0)).
+//
+// One CTA per SM (persistent).  Work item = 128-row block x column segment.  Roles:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane; tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accum in TMEM)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b.x32 -> fma/max/sqrt.approx/add in registers)
+// The 128 x d A block of the item stays resident in shared memory (d <= 512) so only B streams; the
+// accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
+// MMAs of tile t+1.  Algorithmic flops 2*P^2*d per sweep; tensor-bound.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace vtf {
+namespace tc {
+
+constexpr int BM = 128;          // rows per CTA tile (TMEM lanes)
+constexpr int BN = 256;          // columns per MMA tile (TMEM columns per accumulator stage)
+constexpr int BK = 64;           // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 320;    // 2 control warps + 8 epilogue warps
+constexpr int kABlockBytes = BM * BK * 2;   // 16 KB
+constexpr int kBBlockBytes = BN * BK * 2;   // 32 KB
+constexpr unsigned long long kTimeoutCycles = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
+
+struct Params {
+    const float* sqn;
+    const int32_t* chunk_cell;
+    float* cellsum;
+    int64_t P;
+    int64_t rb_begin;
+    int64_t n_rb;
+    int n_kb;            // d / 64
+    int n_seg;           // column segments per row block
+    int tiles_per_seg;   // 256-column tiles per segment
+    int n_tiles;         // P / 256
+    float neg2_inv_s2;   // -2 / scale^2
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const unsigned long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > kTimeoutCycles) __trap();   // a broken pipeline must not hang the device
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// K-major operand, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define VTF_TMEM_LD32(taddr, v)                                                                              \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"    \
+        "%26,%27,%28,%29,%30,%31}, [%32];"                                                                   \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
+        : "r"(taddr))
+
+// the "+r" operands tie every later use of v[] to the completion of the load
+#define VTF_TMEM_WAIT(v)                                                                                     \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                            \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),       \
+                   "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),   \
+                   "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]),             \
+                   "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]),             \
+                   "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]))
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// A_RESIDENT: the item's 128 x d A block is loaded once and kept; otherwise A k-blocks stream with B.
+template <bool A_RESIDENT, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte swizzle needs 1024-byte aligned tiles
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int kStageBytes = kBBlockBytes + (A_RESIDENT ? 0 : kABlockBytes);
+    const uint32_t a_res = base;                                                  // [n_kb][16 KB] when resident
+    const uint32_t stage0 = base + (A_RESIDENT ? (uint32_t)prm.n_kb * kABlockBytes : 0u);
+    const uint32_t bars = stage0 + STAGES * kStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t a_full = bars + 8u * (2 * STAGES);
+    const uint32_t a_empty = a_full + 8u;
+    auto tfull_bar = [&](int s) { return a_empty + 8u + 8u * s; };
+    auto tempty_bar = [&](int s) { return a_empty + 8u + 16u + 8u * s; };
+    const uint32_t tmem_slot = a_empty + 8u + 32u;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int64_t n_items = prm.n_rb * prm.n_seg;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, a_ph = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int64_t rb = prm.rb_begin + item / prm.n_seg;
+                const int seg = (int)(item % prm.n_seg);
+                const int t0 = seg * prm.tiles_per_seg;
+                const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+                if (A_RESIDENT) {
+                    mbar_wait(a_empty, a_ph ^ 1u);
+                    mbar_expect_tx(a_full, (uint32_t)prm.n_kb * kABlockBytes);
+                    for (int kb = 0; kb < prm.n_kb; ++kb)
+                        tma_load_2d(&map_a, a_full, a_res + (uint32_t)kb * kABlockBytes, kb * BK, (int)(rb * BM));
+                    a_ph ^= 1u;
+                }
+                for (int t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < prm.n_kb; ++kb) {
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        mbar_expect_tx(full_bar(s), (uint32_t)kStageBytes);
+                        const uint32_t dst = stage0 + (uint32_t)s * kStageBytes;
+                        tma_load_2d(&map_b, full_bar(s), dst, kb * BK, t * BN);
+                        if (!A_RESIDENT) tma_load_2d(&map_a, full_bar(s), dst + kBBlockBytes, kb * BK, (int)(rb * BM));
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int s = 0, as = 0;
+            uint32_t ph = 0, a_ph = 0, acc_ph = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int seg = (int)(item % prm.n_seg);
+                const int t0 = seg * prm.tiles_per_seg;
+                const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+                if (A_RESIDENT) { mbar_wait(a_full, a_ph); a_ph ^= 1u; }
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(tempty_bar(as), acc_ph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+                    for (int kb = 0; kb < prm.n_kb; ++kb) {
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint32_t b_addr = stage0 + (uint32_t)s * kStageBytes;
+                        const uint32_t a_addr = A_RESIDENT ? a_res + (uint32_t)kb * kABlockBytes : b_addr + kBBlockBytes;
+                        const uint64_t a_desc = make_desc(a_addr), b_desc = make_desc(b_addr);
+#pragma unroll
+                        for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row: start field += 2
+                            tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k4), b_desc + (uint64_t)(2 * k4), kIdesc,
+                                       (uint32_t)((kb | k4) != 0));
+                        }
+                        tc_commit(empty_bar(s));   // frees the smem stage once these MMAs retire
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
+                    tc_commit(tfull_bar(as));       // accumulator complete -> epilogue
+                    if (++as == 2) { as = 0; acc_ph ^= 1u; }
+                }
+                if (A_RESIDENT) tc_commit(a_empty); // A block may be overwritten for the next item
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int q = warp & 3;                 // TMEM lane quarter this warp can read
+        const int half = (warp - 2) >> 2;       // which 128 columns of the 256-wide tile
+        int as = 0;
+        uint32_t acc_ph = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int64_t rb = prm.rb_begin + item / prm.n_seg;
+            const int seg = (int)(item % prm.n_seg);
+            const int t0 = seg * prm.tiles_per_seg;
+            const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+            const int64_t rowbase = rb * BM + q * 32;
+            const int64_t p = rowbase + lane;
+            const float ni = __ldg(prm.sqn + p);
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            int cur_cell = -1;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(tfull_bar(as), acc_ph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int64_t col0 = (int64_t)t * BN + half * 128 + c * 32;
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + (uint32_t)(as * BN + half * 128 + c * 32) + ((uint32_t)(q * 32) << 16);
+                    VTF_TMEM_LD32(taddr, v);
+                    const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
+                    if (cell != cur_cell) {
+                        if (cur_cell >= 0) atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, (acc0 + acc1) + (acc2 + acc3));
+                        acc0 = acc1 = acc2 = acc3 = 0.f;
+                        cur_cell = cell;
+                    }
+                    const float4* nj4 = reinterpret_cast<const float4*>(prm.sqn + col0);
+                    VTF_TMEM_WAIT(v);
+                    const bool diag = (col0 == rowbase);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 nj = __ldg(nj4 + j4);
+                        float r0 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), prm.neg2_inv_s2, ni + nj.x), 0.f));
+                        float r1 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), prm.neg2_inv_s2, ni + nj.y), 0.f));
+                        float r2 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), prm.neg2_inv_s2, ni + nj.z), 0.f));
+                        float r3 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), prm.neg2_inv_s2, ni + nj.w), 0.f));
+                        if (diag) {   // D_pp = 0 (SK/metrics/pairwise.py:2285)
+                            if (lane == 4 * j4 + 0) r0 = 0.f;
+                            if (lane == 4 * j4 + 1) r1 = 0.f;
+                            if (lane == 4 * j4 + 2) r2 = 0.f;
+                            if (lane == 4 * j4 + 3) r3 = 0.f;
+                        }
+                        acc0 += r0; acc1 += r1; acc2 += r2; acc3 += r3;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(as));
+                if (++as == 2) { as = 0; acc_ph ^= 1u; }
+            }
+            if (cur_cell >= 0) atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, (acc0 + acc1) + (acc2 + acc3));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* Xh, int64_t P, int d, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(VTF_ERR_CUDA, "vtf_sil_sweep", "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(Xh), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return fail(VTF_ERR_CUDA, "vtf_sil_sweep", buf);
+    }
+    return VTF_OK;
+}
+
+template <bool A_RES, int STAGES>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& prm, int grid, void* stream) {
+    const size_t stage = kBBlockBytes + (A_RES ? 0 : kABlockBytes);
+    const size_t smem = 1024 + (A_RES ? (size_t)prm.n_kb * kABlockBytes : 0) + STAGES * stage + 256;
+    VTF_CUDA(cudaFuncSetAttribute(sil_sweep_kernel<A_RES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "vtf_sil_sweep/smem");
+    VTF_LAUNCH((sil_sweep_kernel<A_RES, STAGES>), grid, kThreads, smem, stream, ma, mb, prm);
+    VTF_CHECK_LAST("vtf_sil_sweep");
+    return VTF_OK;
+}
+
+}  // namespace tc
+}  // namespace vtf
+
+using namespace vtf;
+
+extern "C" int vtf_sil_sweep(const void* Xh, const float* sqn, int64_t P, int d, float scale, const int32_t* chunk_cell,
+                             int n_cells, int64_t rb_begin, int64_t rb_end, float* cellsum, void* stream) {
+    VTF_REQUIRE(Xh && sqn && chunk_cell && cellsum && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0 &&
+                    n_cells > 0 && rb_begin >= 0 && rb_end <= P / tc::BM && scale > 0.f,
+                "vtf_sil_sweep (P % 256 == 0, d % 64 == 0, 64 <= d <= 1024)");
+    if (rb_end <= rb_begin) return VTF_OK;
+    int rc = vtf_device_check();
+    if (rc != VTF_OK) return rc;
+    CUtensorMap ma, mb;
+    if ((rc = tc::make_map(&ma, Xh, P, d, tc::BM)) != VTF_OK) return rc;
+    if ((rc = tc::make_map(&mb, Xh, P, d, tc::BN)) != VTF_OK) return rc;
+    tc::Params prm;
+    prm.sqn = sqn; prm.chunk_cell = chunk_cell; prm.cellsum = cellsum; prm.P = P;
+    prm.rb_begin = rb_begin; prm.n_rb = rb_end - rb_begin;
+    prm.n_kb = d / tc::BK;
+    prm.n_tiles = (int)(P / tc::BN);
+    const int sms = num_sms();
+    // enough items to fill the machine twice when the row blocks alone cannot
+    int n_seg = 1;
+    if (prm.n_rb < 2 * (int64_t)sms) n_seg = (int)min((int64_t)prm.n_tiles, (2 * (int64_t)sms + prm.n_rb - 1) / prm.n_rb);
+    prm.tiles_per_seg = (prm.n_tiles + n_seg - 1) / n_seg;
+    prm.n_seg = (prm.n_tiles + prm.tiles_per_seg - 1) / prm.tiles_per_seg;
+    prm.neg2_inv_s2 = -2.f / (scale * scale);
+    const int grid = (int)min((int64_t)sms, prm.n_rb * prm.n_seg);
+    if (d <= 512) return tc::launch<true, 3>(ma, mb, prm, grid, stream);
+    return tc::launch<false, 4>(ma, mb, prm, grid, stream);
+}

@@ -1,0 +1,193 @@
+// Row/column pre-passes of the grouping path: one coalesced, vectorised read of X each.
+//   normalize_rows  <- sklearn normalize() inside cosine_distances (dupes.py:60, grouping.py:51)
+//   col_stats/center_rows <- KMeans.fit set-up (SK/cluster/_kmeans.py:1473-1490)
+//   gather_rows     <- np.delete (dupes.py:68)
+// All HBM-bound: algorithmic bytes are N*d*4 read (+ N*d*4 written where a copy is produced).
+#include "common.cuh"
+
+namespace vtf {
+
+thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
+
+int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ---------------------------------------------------------------------------------------
+// warp per row: |x|^2 in fp32 (lanes own interleaved float4 columns), optional normalise.
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ X, int64_t N, int d,
+                                                       float* __restrict__ Xn, float* __restrict__ sqn) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = d >> 2;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (; row < N; row += stride) {
+        const float4* xr = reinterpret_cast<const float4*>(X + row * d);
+        float s = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+            float4 a = ldg_stream(xr + v);
+            s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+        }
+        s = warp_sum(s);
+        if (sqn && lane == 0) sqn[row] = s;
+        if (NORMALIZE) {
+            float nrm = sqrtf(s);
+            // SK/preprocessing/_data.py:127-132: norms below 10*eps are replaced by 1
+            if (nrm < 10.f * 1.1920929e-07f) nrm = 1.f;
+            float4* outr = reinterpret_cast<float4*>(Xn + row * d);
+            for (int v = lane; v < nvec; v += 32) {
+                float4 a = __ldg(xr + v);   // second touch comes from L1/L2
+                a.x = __fdiv_rn(a.x, nrm); a.y = __fdiv_rn(a.y, nrm);
+                a.z = __fdiv_rn(a.z, nrm); a.w = __fdiv_rn(a.w, nrm);
+                outr[v] = a;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums / sums of squares in fp64: thread owns one float4 column, blocks stride rows.
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ X, int64_t N, int d,
+                                                        double* __restrict__ part) {
+    const int nvec = d >> 2;
+    double* mypart = part + (size_t)blockIdx.x * 2 * d;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        int64_t r = blockIdx.x;
+        const int64_t step = gridDim.x;
+        for (; r + 3 * step < N; r += 4 * step) {
+            float4 a0 = ldg_stream(reinterpret_cast<const float4*>(X + r * d) + v);
+            float4 a1 = ldg_stream(reinterpret_cast<const float4*>(X + (r + step) * d) + v);
+            float4 a2 = ldg_stream(reinterpret_cast<const float4*>(X + (r + 2 * step) * d) + v);
+            float4 a3 = ldg_stream(reinterpret_cast<const float4*>(X + (r + 3 * step) * d) + v);
+#define VTF_ACC(a)                                                                     \
+    s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;                                \
+    q[0] += (double)a.x * a.x; q[1] += (double)a.y * a.y;                              \
+    q[2] += (double)a.z * a.z; q[3] += (double)a.w * a.w;
+            VTF_ACC(a0) VTF_ACC(a1) VTF_ACC(a2) VTF_ACC(a3)
+        }
+        for (; r < N; r += step) {
+            float4 a0 = ldg_stream(reinterpret_cast<const float4*>(X + r * d) + v);
+            VTF_ACC(a0)
+        }
+#undef VTF_ACC
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mypart[4 * v + j] = s[j];
+            mypart[d + 4 * v + j] = q[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) center_kernel(const float4* __restrict__ X, int64_t nvec_total, int nvec,
+                                                     const float4* __restrict__ mean, float4* __restrict__ Xc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nvec_total; i += stride) {
+        float4 a = ldg_stream(X + i);
+        float4 m = __ldg(mean + (i % nvec));
+        a.x -= m.x; a.y -= m.y; a.z -= m.z; a.w -= m.w;
+        Xc[i] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, int d, const int64_t* __restrict__ idx,
+                                                          int64_t n_out, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = d >> 2;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (; row < n_out; row += stride) {
+        const float4* src = reinterpret_cast<const float4*>(X + idx[row] * d);
+        float4* dst = reinterpret_cast<float4*>(out + row * d);
+        for (int v = lane; v < nvec; v += 32) dst[v] = ldg_stream(src + v);
+    }
+}
+
+static int col_stats_grid() { return num_sms() * 8; }
+
+}  // namespace vtf
+
+using namespace vtf;
+
+extern "C" {
+
+int vtf_version(void) { return 100; }
+const char* vtf_last_error(void) { return g_err; }
+int64_t vtf_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int vtf_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(VTF_ERR_DEVICE, "vtf_device_check", cudaGetErrorString(e));
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "compute capability %d.%d, need 10.x (B200)", major, minor);
+        return fail(VTF_ERR_DEVICE, "vtf_device_check", buf);
+    }
+    return VTF_OK;
+}
+
+int vtf_normalize_rows(const float* X, int64_t N, int d, float* Xn, void* stream) {
+    VTF_REQUIRE(X && Xn && N >= 0 && d > 0 && d % 4 == 0, "vtf_normalize_rows");
+    if (N == 0) return VTF_OK;
+    int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    VTF_LAUNCH(row_norm_kernel<true>, grid, 256, 0, stream, X, N, d, Xn, (float*)nullptr);
+    VTF_CHECK_LAST("vtf_normalize_rows");
+    return VTF_OK;
+}
+
+int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* stream) {
+    VTF_REQUIRE(X && sqnorm && N >= 0 && d > 0 && d % 4 == 0, "vtf_row_sqnorms");
+    if (N == 0) return VTF_OK;
+    int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    VTF_LAUNCH(row_norm_kernel<false>, grid, 256, 0, stream, X, N, d, (float*)nullptr, sqnorm);
+    VTF_CHECK_LAST("vtf_row_sqnorms");
+    return VTF_OK;
+}
+
+size_t vtf_col_stats_ws_bytes(int d) { return (size_t)col_stats_grid() * 2 * (size_t)d * sizeof(double); }
+
+int vtf_col_stats(const float* X, int64_t N, int d, double* col_sum, double* col_sumsq, void* ws, void* stream) {
+    VTF_REQUIRE(X && col_sum && col_sumsq && ws && N >= 0 && d > 0 && d % 4 == 0, "vtf_col_stats");
+    const int grid = col_stats_grid();
+    int threads = min(256, ((d / 4 + 31) / 32) * 32);
+    VTF_LAUNCH(col_stats_kernel, grid, threads, 0, stream, X, N, d, (double*)ws);
+    VTF_CHECK_LAST("vtf_col_stats");
+    VTF_LAUNCH(reduce_parts_kernel, (2 * d + 255) / 256, 256, 0, stream, (const double*)ws, grid, 2 * d, col_sum,
+               col_sumsq, d);
+    VTF_CHECK_LAST("vtf_col_stats/reduce");
+    return VTF_OK;
+}
+
+int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* Xc, void* stream) {
+    VTF_REQUIRE(X && Xc && mean && N >= 0 && d > 0 && d % 4 == 0, "vtf_center_rows");
+    if (N == 0) return VTF_OK;
+    int64_t nvt = N * (d / 4);
+    int grid = (int)min((int64_t)num_sms() * 16, (nvt + 255) / 256);
+    VTF_LAUNCH(center_kernel, grid, 256, 0, stream, (const float4*)X, nvt, d / 4, (const float4*)mean, (float4*)Xc);
+    VTF_CHECK_LAST("vtf_center_rows");
+    return VTF_OK;
+}
+
+int vtf_gather_rows(const float* X, int d, const int64_t* idx, int64_t n_out, float* X_out, void* stream) {
+    VTF_REQUIRE(X && idx && X_out && n_out >= 0 && d > 0 && d % 4 == 0, "vtf_gather_rows");
+    if (n_out == 0) return VTF_OK;
+    int grid = (int)min((int64_t)num_sms() * 8, (n_out + 7) / 8);
+    VTF_LAUNCH(gather_rows_kernel, grid, 256, 0, stream, X, d, idx, n_out, X_out);
+    VTF_CHECK_LAST("vtf_gather_rows");
+    return VTF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Rows-against-a-small-matrix kernels: the Lloyd E-step and nearest-reference classification.
+//   lloyd_assign    <- SK/cluster/_k_means_lloyd.pyx:168-218 (SGEMM chunk + first-index argmin)
+//   cosine_classify <- grouping.py:51-56 over SK/metrics/pairwise.py:1697-1752
+// HBM-bound for the k / R these calls see (k <= 32, R ~ 32): one coalesced 128-bit read of each
+// row, the small matrix staged once per CTA in shared memory, fp32 FMA dot products per lane
+// and a shuffle reduction.  Algorithmic bytes: N*d*4 (+ N*R*4 for the distance log).
+#include "common.cuh"
+
+namespace vtf {
+
+constexpr int kRowsPerWarp = 2;
+constexpr int kMaxDV = 8;   // register-cached rows up to d = 1024
+
+struct LloydEpi {
+    int32_t* labels;
+    unsigned long long* counts;
+    unsigned long long* n_changed;
+};
+struct ClassifyEpi {
+    float* dist;
+    int64_t* label;
+    float thr;       // < 0 or NaN: disabled
+};
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    return acc;
+}
+
+// MODE 0: Lloyd (score = |c|^2 - 2 x.c), MODE 1: classify (score = clip(1 - x.c, 0, 2))
+template <int MODE, int DV, bool C_SMEM>
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X, int64_t N, int d,
+                                                     const float* __restrict__ C, int k,
+                                                     LloydEpi le, ClassifyEpi ce) {
+    extern __shared__ __align__(16) float smem[];
+    float* sC = smem;                          // [k*d] when C_SMEM
+    float* sC2 = smem + (C_SMEM ? (size_t)k * d : 0);   // [k] squared norms (Lloyd)
+    __shared__ unsigned int s_changed;
+    unsigned int* s_counts = reinterpret_cast<unsigned int*>(sC2 + k);   // [k]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nvec = d >> 2;
+
+    if (C_SMEM) {
+        const float4* Cg = reinterpret_cast<const float4*>(C);
+        float4* Cs = reinterpret_cast<float4*>(sC);
+        for (int i = threadIdx.x; i < k * nvec; i += blockDim.x) Cs[i] = __ldg(Cg + i);
+    }
+    if (threadIdx.x == 0) s_changed = 0;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) s_counts[c] = 0;
+    __syncthreads();
+    if (MODE == 0) {
+        // |c|^2 per centre, one warp per centre (fp32, as SK/cluster/_k_means_lloyd.pyx:99)
+        for (int c = warp; c < k; c += nwarps) {
+            const float4* cr = reinterpret_cast<const float4*>(C_SMEM ? sC + (size_t)c * d : C + (size_t)c * d);
+            float s = 0.f;
+            for (int v = lane; v < nvec; v += 32) { float4 a = cr[v]; s = dot4(a, a, s); }
+            s = warp_sum(s);
+            if (lane == 0) sC2[c] = s;
+        }
+        __syncthreads();
+    }
+
+    unsigned int my_changed = 0;
+    const int64_t warps_total = (int64_t)gridDim.x * nwarps;
+    for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * kRowsPerWarp; row0 < N;
+         row0 += warps_total * kRowsPerWarp) {
+        const bool has1 = (row0 + 1 < N);
+        const float4* x0p = reinterpret_cast<const float4*>(X + row0 * d);
+        const float4* x1p = reinterpret_cast<const float4*>(X + (has1 ? row0 + 1 : row0) * d);
+        float4 x0[DV > 0 ? DV : 1], x1[DV > 0 ? DV : 1];
+        if (DV > 0) {
+#pragma unroll
+            for (int v = 0; v < DV; ++v) { x0[v] = ldg_stream(x0p + lane + 32 * v); x1[v] = ldg_stream(x1p + lane + 32 * v); }
+        }
+        float best0 = INFINITY, best1 = INFINITY;
+        int arg0 = 0, arg1 = 0;
+        float keep0 = 0.f, keep1 = 0.f;   // classify: lane (c & 31) keeps distance c for the coalesced store
+        for (int c = 0; c < k; ++c) {
+            const float4* cr = reinterpret_cast<const float4*>(C_SMEM ? sC + (size_t)c * d : C + (size_t)c * d);
+            float p0 = 0.f, p1 = 0.f;
+            if (DV > 0) {
+#pragma unroll
+                for (int v = 0; v < DV; ++v) {
+                    float4 cv = C_SMEM ? cr[lane + 32 * v] : __ldg(cr + lane + 32 * v);
+                    p0 = dot4(x0[v], cv, p0); p1 = dot4(x1[v], cv, p1);
+                }
+            } else {
+                for (int v = lane; v < nvec; v += 32) {
+                    float4 cv = C_SMEM ? cr[v] : __ldg(cr + v);
+                    p0 = dot4(__ldg(x0p + v), cv, p0); p1 = dot4(__ldg(x1p + v), cv, p1);
+                }
+            }
+            p0 = warp_sum(p0); p1 = warp_sum(p1);
+            float s0, s1;
+            if (MODE == 0) {
+                const float c2 = sC2[c];
+                s0 = fmaf(-2.f, p0, c2); s1 = fmaf(-2.f, p1, c2);
+            } else {
+                s0 = fminf(fmaxf(1.f - p0, 0.f), 2.f); s1 = fminf(fmaxf(1.f - p1, 0.f), 2.f);
+                if ((c & 31) == lane) { keep0 = s0; keep1 = s1; }
+                if ((c & 31) == 31 || c == k - 1) {
+                    const int cb = c & ~31;
+                    if (cb + lane <= c) {
+                        ce.dist[row0 * k + cb + lane] = keep0;
+                        if (has1) ce.dist[(row0 + 1) * k + cb + lane] = keep1;
+                    }
+                }
+            }
+            if (s0 < best0) { best0 = s0; arg0 = c; }   // strict '<': first index wins
+            if (s1 < best1) { best1 = s1; arg1 = c; }
+        }
+        if (lane == 0) {
+            if (MODE == 0) {
+                if (le.labels[row0] != arg0) ++my_changed;
+                le.labels[row0] = arg0;
+                atomicAdd(&s_counts[arg0], 1u);
+                if (has1) {
+                    if (le.labels[row0 + 1] != arg1) ++my_changed;
+                    le.labels[row0 + 1] = arg1;
+                    atomicAdd(&s_counts[arg1], 1u);
+                }
+            } else {
+                const bool on = ce.thr >= 0.f;   // false for NaN as well
+                ce.label[row0] = (on && best0 >= ce.thr) ? (int64_t)k : (int64_t)arg0;
+                if (has1) ce.label[row0 + 1] = (on && best1 >= ce.thr) ? (int64_t)k : (int64_t)arg1;
+            }
+        }
+    }
+    if (MODE == 0) {
+        if (lane == 0 && my_changed) atomicAdd(&s_changed, my_changed);
+        __syncthreads();
+        for (int c = threadIdx.x; c < k; c += blockDim.x)
+            if (s_counts[c]) atomicAdd(le.counts + c, (unsigned long long)s_counts[c]);
+        if (threadIdx.x == 0 && s_changed) atomicAdd(le.n_changed, (unsigned long long)s_changed);
+    }
+}
+
+template <int MODE>
+static int launch_rowdot(const float* X, int64_t N, int d, const float* C, int k, LloydEpi le, ClassifyEpi ce,
+                         void* stream, const char* what) {
+    const size_t small = (size_t)k * (sizeof(float) + sizeof(unsigned int));
+    const size_t c_bytes = (size_t)k * d * sizeof(float);
+    const bool c_smem = (c_bytes + small) <= 200 * 1024;
+    const size_t smem = (c_smem ? c_bytes : 0) + small;
+    const int dv = (d % 128 == 0 && d / 128 <= kMaxDV) ? d / 128 : 0;
+    int blocks_per_sm = c_smem ? (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / (smem + 1024))) : 4;
+    int64_t want = (N + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp);
+    int grid = (int)max((int64_t)1, min((int64_t)num_sms() * blocks_per_sm, want));
+
+#define VTF_RD_CASE(DVv)                                                                               \
+    case DVv:                                                                                          \
+        if (c_smem) {                                                                                  \
+            VTF_CUDA(cudaFuncSetAttribute(rowdot_kernel<MODE, DVv, true>,                              \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what); \
+            VTF_LAUNCH((rowdot_kernel<MODE, DVv, true>), grid, 256, smem, stream, X, N, d, C, k, le, ce); \
+        } else {                                                                                       \
+            VTF_LAUNCH((rowdot_kernel<MODE, DVv, false>), grid, 256, smem, stream, X, N, d, C, k, le, ce); \
+        }                                                                                              \
+        break;
+    switch (dv) {
+        VTF_RD_CASE(0) VTF_RD_CASE(1) VTF_RD_CASE(2) VTF_RD_CASE(3) VTF_RD_CASE(4)
+        VTF_RD_CASE(5) VTF_RD_CASE(6) VTF_RD_CASE(7) VTF_RD_CASE(8)
+    }
+#undef VTF_RD_CASE
+    VTF_CHECK_LAST(what);
+    return VTF_OK;
+}
+
+}  // namespace vtf
+
+using namespace vtf;
+
+extern "C" {
+
+int vtf_lloyd_assign(const float* Xc, int64_t N, int d, const float* C, int k, int32_t* labels, int64_t* counts,
+                     int64_t* n_changed, void* stream) {
+    VTF_REQUIRE(Xc && C && labels && counts && n_changed && N >= 0 && d > 0 && d % 4 == 0 && k > 0,
+                "vtf_lloyd_assign");
+    if (N == 0) return VTF_OK;
+    LloydEpi le{labels, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(n_changed)};
+    ClassifyEpi ce{nullptr, nullptr, -1.f};
+    return launch_rowdot<0>(Xc, N, d, C, k, le, ce, stream, "vtf_lloyd_assign");
+}
+
+int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int R, float thr, float* dist,
+                        int64_t* label, void* stream) {
+    VTF_REQUIRE(Xn && Rn && dist && label && N >= 0 && d > 0 && d % 4 == 0 && R > 0, "vtf_cosine_classify");
+    if (N == 0) return VTF_OK;
+    LloydEpi le{nullptr, nullptr, nullptr};
+    ClassifyEpi ce{dist, label, thr};
+    return launch_rowdot<1>(Xn, N, d, Rn, R, le, ce, stream, "vtf_cosine_classify");
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""ctypes binding of libvtf_b200.so (include/vtf_b200.h).
+
+The library is the only compute back end: if it is missing, or no sm_100 GPU is visible, every
+entry point raises -- there is no CPU fallback (BASELINE.json north_star).
+"""
+import ctypes
+import os
+import os.path as osp
+
+c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+LIB_PATH = osp.join(osp.dirname(osp.abspath(__file__)), '_lib', 'libvtf_b200.so')
+
+# name -> (restype, argtypes); mirrors include/vtf_b200.h one to one (tests/test_cabi.py checks it)
+SIGNATURES = {
+    'vtf_version': (c_int, []),
+    'vtf_last_error': (ctypes.c_char_p, []),
+    'vtf_launch_count': (c_i64, []),
+    'vtf_device_check': (c_int, []),
+    'vtf_normalize_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    'vtf_col_stats_ws_bytes': (c_sz, [c_int]),
+    'vtf_col_stats': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_center_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    'vtf_kpp_ws_bytes': (c_sz, [c_int]),
+    'vtf_kpp_dist': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_kpp_pick': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_lloyd_assign': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_cluster_sums_ws_bytes': (c_sz, [c_int, c_int]),
+    'vtf_cluster_sums': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'vtf_cluster_dispersion': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_lloyd_update': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
+    'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
+    'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    'vtf_gather_rows': (c_int, [c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
+    'vtf_silhouette_rowsums_exact': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
+    'vtf_row_sqnorms': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    'vtf_sil_pack': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    'vtf_absmax': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    'vtf_sil_sweep': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
+    'vtf_sil_finish_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'vtf_sil_finish_cells': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed for loading / symbol checks)."""
+    global _lib
+    if _lib is None:
+        if not osp.exists(LIB_PATH):
+            raise NativeError('CUDA extension %s is missing: run `python video-to-faces_b200/build.py` '
+                              '(there is no CPU fallback)' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().vtf_last_error().decode('utf-8', 'replace')
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a negative status."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise NativeError('%s failed (%d): %s' % (name, rc, last_error()))
+
+
+def launch_count():
+    return int(load().vtf_launch_count())
+
+
+def require_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError('videotofaces_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    call('vtf_device_check')
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, None -> NULL."""
+    return None if t is None else c_vp(t.data_ptr())
+
+
+def stream():
+    import torch
+    return c_vp(torch.cuda.current_stream().cuda_stream)

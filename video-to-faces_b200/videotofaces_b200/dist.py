@@ -1,0 +1,74 @@
+"""Row sharding of the grouping path over the GPUs of one box.
+
+The reference is single-process (no NCCL/MPI anywhere); this is new.  One process per GPU, every
+rank holds the full embedding matrix (2-12 GB against 180 GB of HBM) and computes a row shard of
+every phase.  Exchange steps, all through torch.distributed (NCCL over NVLink; gloo in CPU tests):
+
+  K-means prologue   all-reduce  column sums / sums of squares            2*d fp64
+  k-means++ round    all-reduce  candidate potentials (T fp64)
+                     all-gather  closest-distance shard (N fp32 in total)
+  Lloyd iteration    all-reduce  centroid sums + counts + changed         (k*d + k + 1) fp64
+  dedup              all-reduce(min) of the packed (distance, argmin) keys  N int64
+  silhouette / CH / DB  all-reduce of n_labellings (or 2k + k*d) fp64 partial sums
+"""
+import torch
+
+
+class Comm:
+    """Thin wrapper: a no-op for one rank, torch.distributed collectives otherwise."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.active = dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.world = dist.get_world_size(group) if self.active else 1
+        if self.world == 1:
+            self.active = False
+
+    def allreduce_sum(self, t):
+        if self.active:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_min(self, t):
+        if self.active:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def allgather_rows(self, full, bounds):
+        """`full` is a [N, ...] tensor of which this rank filled rows bounds[rank]:bounds[rank+1];
+        afterwards every rank holds all rows.  Shards may be ragged."""
+        if not self.active:
+            return full
+        parts = [full[bounds[r]:bounds[r + 1]] for r in range(self.world)]
+        if len({p.shape[0] for p in parts}) == 1:
+            self._dist.all_gather(parts, parts[self.rank].clone(), group=self.group)
+        else:
+            for r in range(self.world):
+                self._dist.broadcast(parts[r], src=self._global(r), group=self.group)
+        return full
+
+    def _global(self, r):
+        return r if self.group is None else self._dist.get_global_rank(self.group, r)
+
+    def barrier(self):
+        if self.active:
+            self._dist.barrier(group=self.group)
+
+
+def shard_bounds(n, world, align=1):
+    """Contiguous shards of `n` units, each boundary a multiple of `align` (last one ragged)."""
+    units = (n + align - 1) // align
+    base, rem = divmod(units, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(min(n, (bounds[-1] // align + base + (1 if r < rem else 0)) * align))
+    bounds[-1] = n
+    return bounds
+
+
+def cyclic_tiles(n_tiles, rank, world):
+    """Tiles rank, rank+world, ...: balances the triangular dedup work (hard part 6)."""
+    return list(range(rank, n_tiles, world))

@@ -1,0 +1,414 @@
+"""Host orchestration of the grouping hot path on B200 (one process per GPU).
+
+Mirrors, stage by stage, what the reference delegates to scikit-learn 1.9.0 ("SK/" below is
+site-packages/sklearn; reference lines are /root/reference/src/videotofaces/...):
+
+  dedup()           dupes.py:60-65        cosine_distances + masked min/argmin + threshold
+  classify()        grouping.py:51-56     cosine_distances + argmin + 'other' threshold
+  kmeans_sweep()    grouping.py:99-101    KMeans(k, random_state, n_init='auto').fit for every k
+  cluster_scores()  grouping.py:104-108   silhouette / calinski-harabasz / davies-bouldin per k
+
+Only O(k), O(d) and O(trials) scalars ever come back to the host inside these loops (convergence
+flags, candidate potentials, RNG draws); all O(N) work is in the kernels of csrc/.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .dist import Comm, shard_bounds
+
+TC_MIN_ROWS = 4096        # below this the exact fp32 silhouette kernel is used (and is fast enough)
+TC_MAX_CELLSUM_BYTES = 32 << 30
+
+
+class KMeansResult:
+    __slots__ = ('k', 'labels', 'centers', 'inertia', 'n_iter', 'seeds', 'counts', 'strict')
+
+    def __init__(self, **kw):
+        for n in self.__slots__:
+            setattr(self, n, kw.get(n))
+
+
+class FitContext:
+    """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
+    __slots__ = ('X', 'Xc', 'N', 'd', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol')
+
+
+def n_local_trials(k):
+    return 2 + int(math.log(k))                                            # SK/cluster/_kmeans.py:228
+
+
+def _ceil_to_f32(v64):
+    """Smallest fp32 >= v (searchsorted compares the fp32 cumsum with fp64 thresholds, _kmeans.py:250)."""
+    t = np.asarray(v64, dtype=np.float64).astype(np.float32)
+    low = t.astype(np.float64) < v64
+    t[low] = np.nextafter(t[low], np.float32(np.inf))
+    return t
+
+
+class GroupingEngine:
+    def __init__(self, kernels, comm=None):
+        self.K = kernels
+        self.comm = comm if comm is not None else Comm()
+        self.device = kernels.device
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------ utilities
+    def to_device(self, A, dtype=torch.float32):
+        if isinstance(A, torch.Tensor):
+            return A.to(device=self.device, dtype=dtype).contiguous()
+        A = np.ascontiguousarray(A, dtype={torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64}[dtype])
+        return torch.from_numpy(A).to(self.device, non_blocking=False)
+
+    def _bounds(self, n, align=1):
+        return shard_bounds(n, self.comm.world, align)
+
+    # ------------------------------------------------------------------------------ a1 dedup
+    def dedup(self, X, threshold):
+        """dupes.py:60-65.  Returns (mins fp32 [N], inds int64 [N], idx int64 [n_dup]) as numpy."""
+        X = self.to_device(X)
+        N = X.shape[0]
+        if N == 0:
+            return np.zeros(0, np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        Xn = self.K.normalize_rows(X)
+        key = self.K.cosine_dedup(Xn, self.comm.rank, self.comm.world)
+        self.comm.allreduce_min(key)
+        key_h = key.cpu().numpy()
+        mins = (key_h >> 32).astype(np.uint32).view(np.float32)
+        inds = (key_h & 0xffffffff).astype(np.int64)
+        idx = (mins <= np.float32(threshold)).nonzero()[0]                    # dupes.py:65, fp32 compare
+        return mins, inds, idx
+
+    def delete_rows(self, X, idx):
+        """np.delete(X, idx, axis=0) (dupes.py:68) on the device; returns a device tensor."""
+        X = self.to_device(X)
+        keep = np.ones(X.shape[0], dtype=bool)
+        keep[idx] = False
+        kept = torch.from_numpy(np.nonzero(keep)[0].astype(np.int64)).to(self.device)
+        return self.K.gather_rows(X, kept)
+
+    # ------------------------------------------------------------------------------ a3 classify
+    def classify(self, X, R, thr):
+        """grouping.py:51-56.  Returns (dist fp32 [N,R], inds int64 [N]) as numpy."""
+        X = self.to_device(X)
+        R = self.to_device(R)
+        Xn = self.K.normalize_rows(X)
+        Rn = self.K.normalize_rows(R)
+        b, e = self._my_rows(X.shape[0])
+        on = bool(thr) and thr != -1                                          # grouping.py:53
+        nR = R.shape[0]
+        dist = self.K.zeros((X.shape[0], nR), torch.float32) if self.comm.active else None
+        label = self.K.zeros((X.shape[0],), torch.int64) if self.comm.active else None
+        d_loc, l_loc = self.K.cosine_classify(Xn[b:e], Rn, float(thr) if on else -1.0)
+        if self.comm.active:
+            dist[b:e] = d_loc
+            label[b:e] = l_loc
+            bounds = self._bounds(X.shape[0])
+            self.comm.allgather_rows(dist, bounds)
+            self.comm.allgather_rows(label, bounds)
+        else:
+            dist, label = d_loc, l_loc
+        return dist.cpu().numpy(), label.cpu().numpy()
+
+    def _my_rows(self, n, align=1):
+        bounds = self._bounds(n, align)
+        return bounds[self.comm.rank], bounds[self.comm.rank + 1]
+
+    # ------------------------------------------------------------------------------ a6 prologue
+    def prepare(self, X):
+        X = self.to_device(X)
+        ctx = FitContext()
+        ctx.X, ctx.N, ctx.d = X, X.shape[0], X.shape[1]
+        ctx.bounds = self._bounds(ctx.N)
+        ctx.b, ctx.e = ctx.bounds[self.comm.rank], ctx.bounds[self.comm.rank + 1]
+        s, q = self.K.col_stats(X[ctx.b:ctx.e])
+        sq = torch.cat([s, q])
+        self.comm.allreduce_sum(sq)
+        s, q = sq[:ctx.d], sq[ctx.d:]
+        ctx.col_sum = s
+        ctx.mean64 = s / ctx.N
+        ctx.mean32 = ctx.mean64.to(torch.float32)
+        var = q / ctx.N - ctx.mean64 * ctx.mean64                              # np.var(X, axis=0), _kmeans.py:292
+        ctx.tol = float(var.clamp_min(0).mean().item()) * 1e-4                 # _kmeans.py:293, tol=1e-4
+        ctx.Xc = self.K.center_rows(X, ctx.mean32)                             # _kmeans.py:1487-1490
+        return ctx
+
+    # ------------------------------------------------------------------------------ a7 k-means++
+    def kmeans_plusplus(self, ctx, k, rstate):
+        """SK/cluster/_kmeans.py:180-278 on the centred matrix; RNG draws come from numpy's MT19937
+        on the host in the reference's order, all O(N) arithmetic runs on the device."""
+        K, comm = self.K, self.comm
+        N, b, e = ctx.N, ctx.b, ctx.e
+        rs = np.random.RandomState(rstate)
+        trials = n_local_trials(k)
+        # rs.choice(N, p=uniform) consumes one random_sample() and picks searchsorted(cdf, u, 'right')
+        first = min(int(rs.random_sample() * N), N - 1)                        # _kmeans.py:231
+        seeds = [first]
+        closest = K.empty((N,), torch.float32)
+        out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None)     # _kmeans.py:240
+        closest[b:e] = out[0]
+        comm.allgather_rows(closest, ctx.bounds)
+        comm.allreduce_sum(pots)
+        pot = np.float32(pots.cpu().numpy()[0])                                # _kmeans.py:243
+        for _ in range(1, k):
+            rand_vals = rs.uniform(size=trials) * np.float64(pot)              # _kmeans.py:249
+            thr = _ceil_to_f32(rand_vals)
+            order = np.argsort(thr, kind='stable')
+            picked = K.kpp_pick(closest, torch.from_numpy(thr[order]).to(self.device)).cpu().numpy()
+            cand = np.empty(trials, dtype=np.int64)
+            cand[order] = picked
+            cand[cand < 0] = N - 1                                             # _kmeans.py:254 clip
+            cand_t = torch.from_numpy(cand).to(self.device)
+            out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand_t), closest[b:e])   # :257-263
+            comm.allreduce_sum(pots)
+            pots32 = pots.cpu().numpy().astype(np.float32)
+            best = int(np.argmin(pots32))                                      # _kmeans.py:266
+            pot = pots32[best]
+            closest[b:e] = out[best]
+            comm.allgather_rows(closest, ctx.bounds)
+            seeds.append(int(cand[best]))
+        return np.asarray(seeds, dtype=np.int64)
+
+    # ------------------------------------------------------------------------------ a6 Lloyd
+    def lloyd(self, ctx, C0, max_iter=300):
+        """SK/cluster/_kmeans.py:629-758 (single Lloyd run) from centred initial centres C0 [k,d]."""
+        K, comm = self.K, self.comm
+        N, d, b, e = ctx.N, ctx.d, ctx.b, ctx.e
+        k = C0.shape[0]
+        C = C0.contiguous().clone()
+        labels = torch.full((N,), -1, dtype=torch.int32, device=self.device)
+        Xs, ls = ctx.Xc[b:e], labels[b:e]
+        red = K.zeros((k * d + k + 1,), torch.float64)
+        strict = False
+        n_iter = 0
+        C64 = None
+        counts = None
+        for it in range(max_iter):
+            counts = K.zeros((k,), torch.int64)
+            n_changed = K.zeros((1,), torch.int64)
+            K.lloyd_assign(Xs, C, ls, counts, n_changed)
+            sums = K.cluster_sums(Xs, ls, k)
+            if comm.active:
+                red[:k * d] = sums.view(-1)
+                red[k * d:k * d + k] = counts.to(torch.float64)
+                red[k * d + k] = n_changed[0].to(torch.float64)
+                comm.allreduce_sum(red)
+                sums = red[:k * d].view(k, d).clone()
+                counts = red[k * d:k * d + k].round().to(torch.int64)
+                n_changed = red[k * d + k:].round().to(torch.int64)
+            C_new, C64, stats = K.lloyd_update(sums, counts, n_changed, C)
+            st = stats.cpu().numpy()                                           # the one D2H of the iteration
+            if (st[2:] == 0).any():
+                C_new, C64, st = self._relocate_empty(ctx, labels, C, sums, counts, n_changed, st)
+            C = C_new                                                          # _kmeans.py:721
+            n_iter = it + 1
+            if st[1] == 0:                                                     # labels == labels_old, :723
+                strict = True
+                break
+            if st[0] <= ctx.tol:                                               # :731-738
+                break
+        if not strict:                                                         # :742-754
+            counts = K.zeros((k,), torch.int64)
+            n_changed = K.zeros((1,), torch.int64)
+            K.lloyd_assign(Xs, C, ls, counts, n_changed)
+            comm.allreduce_sum(counts)
+            C64 = C.to(torch.float64)
+        elif comm.active:
+            pass
+        sq, _, _ = K.cluster_dispersion(Xs, ls, C64)                           # _k_means_common.pyx:94-124
+        comm.allreduce_sum(sq)
+        comm.allgather_rows(labels, ctx.bounds)
+        inertia = float(sq.sum().item())
+        centers = (C + ctx.mean32).contiguous()                                # _kmeans.py:1543-1546
+        return KMeansResult(k=k, labels=labels, centers=centers, inertia=inertia, n_iter=n_iter,
+                            counts=counts, strict=strict)
+
+    def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):
+        """SK/cluster/_k_means_common.pyx:167-211: give every empty cluster the point farthest from
+        its own (old) centre.  Rare; O(k) host steps around one extra pass over X."""
+        K, comm = self.K, self.comm
+        b, e = ctx.b, ctx.e
+        empty = np.nonzero(st[2:] == 0)[0]
+        far = K.empty((ctx.N,), torch.float32)
+        _, _, far_loc = K.cluster_dispersion(ctx.Xc[b:e], labels[b:e], C_old.to(torch.float64), want_far=True)
+        far[b:e] = far_loc
+        comm.allgather_rows(far, ctx.bounds)
+        vals, idxs = torch.topk(far, len(empty))
+        if float(vals[0].item()) == 0.0:                                       # :190-193
+            return K.lloyd_update(sums, counts, n_changed, C_old)[:2] + (st,)
+        comm.allgather_rows(labels, ctx.bounds)
+        sums = sums.clone()
+        counts = counts.clone()
+        for new_id, far_idx in zip(empty.tolist(), idxs.tolist()):
+            old_id = int(labels[far_idx].item())
+            x = ctx.Xc[far_idx].to(torch.float64)
+            sums[old_id] -= x
+            sums[new_id] = x
+            counts[new_id] = 1
+            counts[old_id] -= 1
+        C_new, C64, stats = K.lloyd_update(sums, counts, n_changed, C_old)
+        return C_new, C64, stats.cpu().numpy()
+
+    def kmeans_sweep(self, X, clusters, rstate, inits=None, ctx=None):
+        """grouping.py:99-101 for every k.  `inits[j]` (un-centred [k,d]) replaces k-means++ for k_j.
+
+        Seeds are prefix-shared: every fit starts a fresh RandomState(rstate), so for equal
+        n_local_trials the seed list of k is a prefix of that of k+1."""
+        ctx = ctx if ctx is not None else self.prepare(X)
+        results = []
+        seed_cache = {}
+        if inits is None:
+            by_trials = {}
+            for k in clusters:
+                by_trials.setdefault(n_local_trials(k), []).append(k)
+            for trials, ks in by_trials.items():
+                seed_cache[trials] = self.kmeans_plusplus(ctx, max(ks), rstate)
+        for j, k in enumerate(clusters):
+            if inits is None:
+                seeds = seed_cache[n_local_trials(k)][:k]
+                C0 = self.K.gather_rows(ctx.Xc, torch.from_numpy(seeds).to(self.device))
+            else:
+                seeds = None
+                C0 = (self.to_device(inits[j]) - ctx.mean32).contiguous()
+            res = self.lloyd(ctx, C0)
+            res.seeds = seeds
+            results.append(res)
+        return ctx, results
+
+    # ------------------------------------------------------------------------------ a9 / a10
+    def ch_db_scores(self, ctx, labels, k, counts=None):
+        """calinski_harabasz_score and davies_bouldin_score (SK/metrics/cluster/_unsupervised.py:333-487):
+        one pass for the per-cluster sums, one for the distances to the cluster means."""
+        K, comm = self.K, self.comm
+        b, e = ctx.b, ctx.e
+        if counts is None:
+            counts = torch.bincount(labels.to(torch.int64), minlength=k)
+        sums = K.cluster_sums(ctx.X[b:e], labels[b:e], k)
+        comm.allreduce_sum(sums)
+        cnt = counts.to(torch.float64)
+        means = sums / cnt.clamp_min(1).unsqueeze(1)
+        sq, rt, _ = K.cluster_dispersion(ctx.X[b:e], labels[b:e], means.contiguous())
+        both = torch.cat([sq, rt])
+        comm.allreduce_sum(both)
+        sq, rt = both[:k], both[k:]
+        present = counts > 0
+        n_labels = int(present.sum().item())
+        self._check_n_labels(n_labels, ctx.N)
+        means, cnt, sq, rt = means[present], cnt[present], sq[present], rt[present]
+        # CH (:394-403)
+        extra = float((cnt * ((means - ctx.mean64) ** 2).sum(1)).sum().item())
+        intra = float(sq.sum().item())
+        ch = 1.0 if intra == 0.0 else extra * (ctx.N - n_labels) / (intra * (n_labels - 1.0))
+        # DB (:467-487)
+        intra_d = (rt / cnt).cpu().numpy()
+        m = means.cpu().numpy()
+        cd = np.sqrt(np.maximum(((m[:, None, :] - m[None, :, :]) ** 2).sum(-1), 0.0))
+        if np.allclose(intra_d, 0) or np.allclose(cd, 0):
+            db = 0.0
+        else:
+            cd[cd == 0] = np.inf
+            comb = intra_d[:, None] + intra_d
+            db = float(np.mean(np.max(comb / cd, axis=1)))
+        return float(ch), float(db)
+
+    @staticmethod
+    def _check_n_labels(n_labels, n_samples):
+        if not 1 < n_labels < n_samples:                                       # _unsupervised.py:31-46
+            raise ValueError('Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)' % n_labels)
+
+    # ------------------------------------------------------------------------------ a8 silhouette
+    def silhouette_scores(self, ctx, labels_list, ks, counts_list=None, force=None):
+        """silhouette_score for several labellings of the same X with ONE sweep over the Gram matrix
+        (the reference recomputes all N^2 distances per k, grouping.py:104-105)."""
+        if counts_list is None:
+            counts_list = [torch.bincount(l.to(torch.int64), minlength=k) for l, k in zip(labels_list, ks)]
+        for c in counts_list:
+            self._check_n_labels(int((c > 0).sum().item()), ctx.N)
+        d = ctx.d
+        tc_ok = (d % 64 == 0 and 64 <= d <= 1024)
+        use_tc = tc_ok and ctx.N >= TC_MIN_ROWS if force is None else (force == 'tc')
+        if use_tc and not tc_ok:
+            raise ValueError('tensor-core silhouette needs d % 64 == 0 and 64 <= d <= 1024')
+        if use_tc:
+            return self._silhouette_tc(ctx, labels_list, ks, counts_list)
+        return self._silhouette_exact(ctx, labels_list, ks, counts_list)
+
+    def _silhouette_exact(self, ctx, labels_list, ks, counts_list):
+        K, comm = self.K, self.comm
+        N = ctx.N
+        bounds = self._bounds(N, 64)
+        b, e = bounds[comm.rank], bounds[comm.rank + 1]
+        sqn = K.row_sqnorms(ctx.Xc)
+        out = K.zeros((len(ks),), torch.float64)
+        for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):
+            rowsum = K.zeros((N, k), torch.float64)
+            K.sil_rowsums_exact(ctx.Xc, sqn, lab, k, b, e, rowsum)
+            K.sil_finish_rows(rowsum, lab, cnt, b, e, out[j:j + 1])
+        comm.allreduce_sum(out)
+        return (out / N).cpu().numpy().tolist()
+
+    def build_cells(self, labels_list, ks):
+        """Group rows by their joint label tuple over all labellings ("cells"), pad every cell to a
+        multiple of 32 columns and lay the rows out cell by cell.  Returns
+        (perm int64 [P], chunk_cell int32 [P/32], cell_to_cluster int32 [nL, G], G, P)."""
+        dev = self.device
+        N = labels_list[0].numel()
+        key = torch.zeros(N, dtype=torch.int64, device=dev)
+        span = 1
+        for lab, k in zip(labels_list, ks):
+            if span * k >= (1 << 62):
+                _, key = torch.unique(key, return_inverse=True)
+                span = int(key.max().item()) + 1
+            key = key * k + lab.to(torch.int64)
+            span *= k
+        _, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+        G = cnt.numel()
+        order = torch.argsort(inv, stable=True)
+        pc = ((cnt + 31) // 32) * 32
+        poff = torch.cumsum(pc, 0) - pc
+        start = torch.cumsum(cnt, 0) - cnt
+        total = int(pc.sum().item())
+        P = ((total + 255) // 256) * 256
+        g_sorted = inv[order]
+        dest = poff[g_sorted] + (torch.arange(N, device=dev) - start[g_sorted])
+        perm = torch.full((P,), -1, dtype=torch.int64, device=dev)
+        perm[dest] = order
+        chunk_cell = torch.zeros(P // 32, dtype=torch.int32, device=dev)
+        chunk_cell[:total // 32] = torch.repeat_interleave(torch.arange(G, device=dev, dtype=torch.int32), pc // 32)
+        rep = torch.empty(G, dtype=torch.int64, device=dev)
+        rep[inv] = torch.arange(N, device=dev)
+        c2c = torch.stack([lab[rep].to(torch.int32) for lab in labels_list]).contiguous()
+        return perm, chunk_cell, c2c, G, P
+
+    def _silhouette_tc(self, ctx, labels_list, ks, counts_list):
+        K, comm = self.K, self.comm
+        perm, chunk_cell, c2c, G, P = self.build_cells(labels_list, ks)
+        if G * P * 4 > TC_MAX_CELLSUM_BYTES and len(ks) > 1:
+            h = len(ks) // 2                                                   # too many cells: sweep twice
+            return (self._silhouette_tc(ctx, labels_list[:h], ks[:h], counts_list[:h]) +
+                    self._silhouette_tc(ctx, labels_list[h:], ks[h:], counts_list[h:]))
+        amax = float(K.absmax(ctx.Xc).item())
+        scale = 1.0 if amax <= 0 else 2.0 ** math.floor(math.log2(4096.0 / amax))
+        Xh, sqn = K.sil_pack(ctx.Xc, perm, P, scale)
+        cellsum = K.zeros((G, P), torch.float32)
+        bounds = self._bounds(P // 128, 1)
+        rb0, rb1 = bounds[comm.rank], bounds[comm.rank + 1]
+        K.sil_sweep(Xh, sqn, scale, chunk_cell, G, rb0, rb1, cellsum)
+        out = K.zeros((len(ks),), torch.float64)
+        for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):
+            K.sil_finish_cells(cellsum, c2c[j], k, perm, lab, cnt, rb0 * 128, rb1 * 128, out[j:j + 1])
+        comm.allreduce_sum(out)
+        return (out / ctx.N).cpu().numpy().tolist()
+
+    def cluster_scores(self, ctx, results, force=None):
+        """grouping.py:104-108: [(k, silhouette, CH, DB)] for the KMeans results of a sweep."""
+        ks = [r.k for r in results]
+        labels = [r.labels for r in results]
+        counts = [r.counts for r in results]
+        sil = self.silhouette_scores(ctx, labels, ks, counts, force=force)
+        out = []
+        for r, s in zip(results, sil):
+            ch, db = self.ch_db_scores(ctx, r.labels, r.k, r.counts)
+            out.append((r.k, float(s), ch, db))
+        return out

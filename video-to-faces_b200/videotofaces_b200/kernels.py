@@ -1,0 +1,171 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs/workspaces with torch (device memory and
+streams are torch's job here, nothing else) and launch the hand-written kernels.
+
+Every method takes and returns torch CUDA tensors.  engine.py is written against this interface
+only, which lets the CPU tests drive the sharding logic with a stand-in (tests/fake_kernels.py).
+"""
+import torch
+
+from . import _native as nv
+from ._native import c_f32, c_i64, c_int, ptr, stream
+
+
+class CudaKernels:
+    name = 'cuda-sm100a'
+
+    def __init__(self, device):
+        nv.require_gpu()
+        self.device = torch.device(device)
+        self._ws = None
+
+    # ------------------------------------------------------------------ helpers
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    @staticmethod
+    def _chk(X):
+        assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and X.dim() == 2, 'need contiguous fp32 CUDA [N,d]'
+        assert X.shape[1] % 4 == 0, 'feature dimension must be a multiple of 4'
+        return X.shape[0], X.shape[1]
+
+    # ------------------------------------------------------------------ a2 / prologue
+    def normalize_rows(self, X):
+        N, d = self._chk(X)
+        out = torch.empty_like(X)
+        nv.call('vtf_normalize_rows', ptr(X), c_i64(N), c_int(d), ptr(out), stream())
+        return out
+
+    def row_sqnorms(self, X):
+        N, d = self._chk(X)
+        out = self.empty((N,), torch.float32)
+        nv.call('vtf_row_sqnorms', ptr(X), c_i64(N), c_int(d), ptr(out), stream())
+        return out
+
+    def col_stats(self, X):
+        N, d = self._chk(X)
+        s = self.empty((d,), torch.float64)
+        q = self.empty((d,), torch.float64)
+        ws = self._workspace(nv.load().vtf_col_stats_ws_bytes(d))
+        nv.call('vtf_col_stats', ptr(X), c_i64(N), c_int(d), ptr(s), ptr(q), ptr(ws), stream())
+        return s, q
+
+    def center_rows(self, X, mean32):
+        N, d = self._chk(X)
+        out = torch.empty_like(X)
+        nv.call('vtf_center_rows', ptr(X), c_i64(N), c_int(d), ptr(mean32), ptr(out), stream())
+        return out
+
+    def gather_rows(self, X, idx):
+        N, d = self._chk(X)
+        out = self.empty((idx.numel(), d), torch.float32)
+        nv.call('vtf_gather_rows', ptr(X), c_int(d), ptr(idx), c_i64(idx.numel()), ptr(out), stream())
+        return out
+
+    # ------------------------------------------------------------------ a7
+    def kpp_dist(self, Xc, cand, closest):
+        N, d = self._chk(Xc)
+        T = cand.shape[0]
+        out = self.empty((T, N), torch.float32)
+        pots = self.empty((T,), torch.float64)
+        ws = self._workspace(nv.load().vtf_kpp_ws_bytes(T))
+        nv.call('vtf_kpp_dist', ptr(Xc), c_i64(N), c_int(d), ptr(cand), c_int(T), ptr(closest), ptr(out), ptr(pots),
+                ptr(ws), stream())
+        return out, pots
+
+    def kpp_pick(self, closest, thr32):
+        T = thr32.numel()
+        idx = self.empty((T,), torch.int64)
+        nv.call('vtf_kpp_pick', ptr(closest), c_i64(closest.numel()), ptr(thr32), c_int(T), None, None, ptr(idx), stream())
+        return idx
+
+    # ------------------------------------------------------------------ a6
+    def lloyd_assign(self, Xc, C, labels, counts, n_changed):
+        N, d = self._chk(Xc)
+        nv.call('vtf_lloyd_assign', ptr(Xc), c_i64(N), c_int(d), ptr(C), c_int(C.shape[0]), ptr(labels), ptr(counts),
+                ptr(n_changed), stream())
+
+    def cluster_sums(self, X, labels, k):
+        N, d = self._chk(X)
+        sums = self.empty((k, d), torch.float64)
+        ws = self._workspace(nv.load().vtf_cluster_sums_ws_bytes(k, d))
+        nv.call('vtf_cluster_sums', ptr(X), c_i64(N), c_int(d), ptr(labels), c_int(k), ptr(sums), ptr(ws), stream())
+        return sums
+
+    def cluster_dispersion(self, X, labels, C64, want_far=False):
+        N, d = self._chk(X)
+        k = C64.shape[0]
+        sq = self.empty((k,), torch.float64)
+        rt = self.empty((k,), torch.float64)
+        far = self.empty((N,), torch.float32) if want_far else None
+        ws = self._workspace(nv.load().vtf_cluster_sums_ws_bytes(k, d))
+        nv.call('vtf_cluster_dispersion', ptr(X), c_i64(N), c_int(d), ptr(labels), c_int(k), ptr(C64), ptr(sq), ptr(rt),
+                ptr(far), ptr(ws), stream())
+        return sq, rt, far
+
+    def lloyd_update(self, sums, counts, n_changed, C_old):
+        k, d = C_old.shape
+        C_new = torch.empty_like(C_old)
+        C64 = self.empty((k, d), torch.float64)
+        stats = self.empty((2 + k,), torch.float64)
+        nv.call('vtf_lloyd_update', ptr(sums), ptr(counts), ptr(n_changed), c_int(k), c_int(d), ptr(C_old), ptr(C_new),
+                ptr(C64), ptr(stats), stream())
+        return C_new, C64, stats
+
+    # ------------------------------------------------------------------ a3 / a1
+    def cosine_classify(self, Xn, Rn, thr):
+        N, d = self._chk(Xn)
+        R = Rn.shape[0]
+        dist = self.empty((N, R), torch.float32)
+        label = self.empty((N,), torch.int64)
+        nv.call('vtf_cosine_classify', ptr(Xn), c_i64(N), c_int(d), ptr(Rn), c_int(R), c_f32(thr), ptr(dist), ptr(label),
+                stream())
+        return dist, label
+
+    def cosine_dedup(self, Xn, rank, world):
+        N, d = self._chk(Xn)
+        key = self.empty((N,), torch.int64)
+        nv.call('vtf_dedup_init', ptr(key), c_i64(N), stream())
+        nv.call('vtf_cosine_dedup', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
+        return key
+
+    # ------------------------------------------------------------------ a8
+    def sil_rowsums_exact(self, X, sqn, labels, k, row_begin, row_end, rowsum):
+        N, d = self._chk(X)
+        nv.call('vtf_silhouette_rowsums_exact', ptr(X), ptr(sqn), c_i64(N), c_int(d), ptr(labels), c_int(k),
+                c_i64(row_begin), c_i64(row_end), ptr(rowsum), stream())
+
+    def sil_finish_rows(self, rowsum, labels, counts, row_begin, row_end, out_slot):
+        N, k = rowsum.shape
+        nv.call('vtf_sil_finish_rows', ptr(rowsum), c_i64(N), c_int(k), ptr(labels), ptr(counts), c_i64(row_begin),
+                c_i64(row_end), ptr(out_slot), stream())
+
+    def absmax(self, X):
+        N, d = self._chk(X)
+        out = self.empty((1,), torch.float32)
+        nv.call('vtf_absmax', ptr(X), c_i64(N), c_int(d), ptr(out), stream())
+        return out
+
+    def sil_pack(self, X, perm, P, scale):
+        N, d = self._chk(X)
+        Xh = self.empty((P, d), torch.float16)
+        sqn = self.empty((P,), torch.float32)
+        nv.call('vtf_sil_pack', ptr(X), c_i64(N), c_int(d), ptr(perm), c_i64(P), c_f32(scale), ptr(Xh), ptr(sqn), stream())
+        return Xh, sqn
+
+    def sil_sweep(self, Xh, sqn, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
+        P, d = Xh.shape
+        nv.call('vtf_sil_sweep', ptr(Xh), ptr(sqn), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
+                c_i64(rb_begin), c_i64(rb_end), ptr(cellsum), stream())
+
+    def sil_finish_cells(self, cellsum, cell_to_cluster, k, perm, labels, counts, p_begin, p_end, out_slot):
+        n_cells, P = cellsum.shape
+        nv.call('vtf_sil_finish_cells', ptr(cellsum), c_i64(P), c_int(n_cells), ptr(cell_to_cluster), c_int(k), ptr(perm),
+                ptr(labels), ptr(counts), c_i64(p_begin), c_i64(p_end), ptr(out_slot), stream())

@@ -1,0 +1,64 @@
+"""Seeded synthetic embeddings for the grouping hot path.
+
+The reference has no data generator: real inputs are FaceNet (512-d, unit norm,
+/root/reference/src/videotofaces/encoders/facenet.py:153) or ViT (768/1024-d, LayerNorm output,
+encoders/vit.py:100-101) embeddings.  No encoder weights exist offline, so every test and
+bench line uses these seeded stand-ins; CPU oracle and GPU path read identical bytes.
+"""
+import numpy as np
+
+
+def _normalize_rows(X):
+    n = np.sqrt(np.einsum('ij,ij->i', X, X))
+    n[n == 0] = 1.0
+    return (X / n[:, None]).astype(np.float32)
+
+
+def blobs(N, d, kc=8, noise=1.0, seed=0, normalize=True):
+    """`kc` Gaussian blobs in `d` dims; rows L2-normalised when `normalize` (FaceNet-like)."""
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((kc, d), dtype=np.float32)
+    X = C[rng.integers(0, kc, N)]
+    # generate the noise in slabs so a 1M x 1024 matrix does not need a second full-size temp
+    step = 1 << 16
+    for s in range(0, N, step):
+        e = min(N, s + step)
+        X[s:e] += np.float32(noise) * rng.standard_normal((e - s, d), dtype=np.float32)
+    if normalize:
+        X = _normalize_rows(X)
+    return np.ascontiguousarray(X, dtype=np.float32)
+
+
+def plant_dupes(X, frac=50, seed=1, normalize=True):
+    """Plant m = N/frac near-duplicates: sources in rows < N/2, targets in rows >= N/2.
+
+    x_dst = normalize(x_src + eps * g / sqrt(d)), eps ~ U(0.3, 1.1) so that cosine
+    distances straddle the 0.2 threshold (about 0.04 .. 0.33).  Returns (X, src, dst).
+    """
+    X = X.copy()
+    N, d = X.shape
+    m = max(N // frac, 1) if N >= 4 else 0
+    rng = np.random.default_rng(seed)
+    half = N // 2
+    src = rng.choice(half, size=m, replace=False)
+    dst = half + rng.choice(N - half, size=m, replace=False)
+    eps = rng.uniform(0.3, 1.1, size=m).astype(np.float32)
+    g = rng.standard_normal((m, d), dtype=np.float32)
+    scale = np.sqrt(np.einsum('ij,ij->i', X[src], X[src]))[:, None]
+    Y = X[src] + scale * eps[:, None] * g / np.float32(np.sqrt(d))
+    if normalize:
+        Y = _normalize_rows(Y)
+    X[dst] = Y
+    return X, src, dst
+
+
+def config(name):
+    """The BASELINE.json configs as (kwargs for blobs, extras)."""
+    table = {
+        'c1': dict(N=8, d=512, kc=2, noise=0.5, seed=0, normalize=True),
+        'c2': dict(N=50_000, d=512, kc=8, noise=1.0, seed=0, normalize=True),
+        'c3': dict(N=1_000_000, d=512, kc=8, noise=1.0, seed=0, normalize=True),
+        'c4': dict(N=1_000_000, d=1024, kc=16, noise=1.0, seed=0, normalize=False),
+        'c5': dict(N=4_000_000, d=768, kc=8, noise=1.0, seed=0, normalize=False),
+    }
+    return dict(table[name])
