@@ -1,0 +1,191 @@
+"""-m gpu: every CUDA kernel, called through the C ABI (ctypes -> libvtf_b200.so), against the CPU
+oracle on the same seeded inputs.  Bars: bit-exact / identical for index and label outputs (ties
+reported), 1e-4 relative (BASELINE.json north_star) or tighter for floating point -- the tolerance is
+written at each assert."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_calls as RC
+from oracle import restatement as RS
+from videotofaces_b200.synth import blobs, plant_dupes
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.cuda() if dtype is None else t.to(dtype).cuda()
+
+
+@pytest.fixture(scope='module')
+def K(engine):
+    return engine.K
+
+
+@pytest.mark.parametrize('N,d', [(1, 512), (37, 64), (1000, 512), (513, 768), (260, 1024), (100, 20)])
+def test_normalize_and_norms(K, N, d):
+    rng = np.random.default_rng(N + d)
+    X = rng.standard_normal((N, d), dtype=np.float32) * 3
+    if N > 2:
+        X[1] = 0                                             # zero-norm guard (SK/preprocessing/_data.py:127-132)
+    got = K.normalize_rows(dev(X)).cpu().numpy()
+    np.testing.assert_allclose(got, RS.normalize_l2(X), rtol=1e-6, atol=1e-9)   # norm summed in another order: a few ulp
+    np.testing.assert_allclose(K.row_sqnorms(dev(X)).cpu().numpy(), RS.row_norms_sq(X), rtol=2e-6)
+
+
+@pytest.mark.parametrize('N,d', [(5, 512), (4097, 512), (3000, 768), (2049, 1024), (100, 36)])
+def test_col_stats_center_gather(K, N, d):
+    X = blobs(N, d, kc=3, seed=N, normalize=False) + 0.5
+    s, q = K.col_stats(dev(X))
+    X64 = X.astype(np.float64)
+    np.testing.assert_allclose(s.cpu().numpy(), X64.sum(0), rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(q.cpu().numpy(), (X64 * X64).sum(0), rtol=1e-12)
+    mean32 = (X64.sum(0) / N).astype(np.float32)
+    assert np.array_equal(K.center_rows(dev(X), dev(mean32)).cpu().numpy(), X - mean32)      # bit-exact
+    idx = np.random.default_rng(0).permutation(N)[:max(1, N // 3)].astype(np.int64)
+    assert np.array_equal(K.gather_rows(dev(X), dev(idx)).cpu().numpy(), X[idx])
+
+
+@pytest.mark.parametrize('N,d,T', [(3000, 512, 3), (1025, 768, 2), (700, 1024, 5), (50, 64, 1)])
+def test_kpp_dist_matches_upcast_path(K, N, d, T):
+    X = blobs(N, d, kc=4, seed=7, normalize=(d == 512))
+    Xc = (X - X.mean(0)).astype(np.float32)
+    cand = Xc[np.random.default_rng(1).integers(0, N, T)]
+    want = RS.euclidean_sq_upcast(cand, Xc)
+    out, pots = K.kpp_dist(dev(Xc), dev(cand), None)
+    got = out.cpu().numpy()
+    # fp64 arithmetic rounded once to fp32: identical except where the fp64 sums straddle a rounding boundary
+    assert (got == want).mean() > 0.999
+    # a candidate's distance to itself cancels to ~1e-12 * |x|^2 in fp64 either way: absolute floor
+    np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-9 * float(want.max()))
+    np.testing.assert_allclose(pots.cpu().numpy(), want.sum(1, dtype=np.float64), rtol=1e-7)
+    closest = want[0] * 0.5
+    out2, pots2 = K.kpp_dist(dev(Xc), dev(cand), dev(closest))
+    np.testing.assert_allclose(out2.cpu().numpy(), np.minimum(want, closest[None, :]), rtol=2e-7, atol=1e-9 * float(want.max()))
+
+
+@pytest.mark.parametrize('N', [1, 100, 4096, 4097, 50000])
+def test_kpp_pick_is_the_sequential_fp32_cumsum(K, N):
+    rng = np.random.default_rng(N)
+    closest = (rng.random(N, dtype=np.float32) * 2).astype(np.float32)
+    cs = np.cumsum(closest)                                   # numpy accumulates fp32 sequentially
+    thr = np.sort((rng.random(4) * float(cs[-1])).astype(np.float32))
+    thr[-1] = np.float32(cs[-1] * 2)                          # never reached -> -1 (clipped to N-1 by the host)
+    want = np.searchsorted(cs, thr, side='left').astype(np.int64)
+    want[want >= N] = -1
+    got = K.kpp_pick(dev(closest), dev(thr)).cpu().numpy()
+    assert np.array_equal(got, want)                          # bit-exact: same additions in the same order
+
+
+@pytest.mark.parametrize('N,d,k', [(5000, 512, 6), (3001, 768, 3), (1000, 1024, 32), (33, 64, 2), (2000, 20, 4), (600, 1024, 60)])
+def test_lloyd_assign_and_sums(K, N, d, k):
+    X = blobs(N, d, kc=min(k, 8), seed=11, normalize=(d == 512))
+    Xc = (X - X.mean(0)).astype(np.float32)
+    C = Xc[np.random.default_rng(2).choice(N, k, replace=False)]
+    want = RS.lloyd_assign(Xc, C)
+    labels = torch.full((N,), -1, dtype=torch.int32, device='cuda')
+    counts = torch.zeros(k, dtype=torch.int64, device='cuda')
+    nch = torch.zeros(1, dtype=torch.int64, device='cuda')
+    K.lloyd_assign(dev(Xc), dev(C), labels, counts, nch)
+    got = labels.cpu().numpy()
+    assert (got == want).mean() >= 0.9995, 'label flips beyond fp32 ties'
+    assert int(nch.item()) == N and np.array_equal(counts.cpu().numpy(), np.bincount(got, minlength=k))
+    counts.zero_(); nch.zero_()
+    K.lloyd_assign(dev(Xc), dev(C), labels, counts, nch)
+    assert int(nch.item()) == 0                               # second pass: nothing changes
+    sums = K.cluster_sums(dev(Xc), labels, k).cpu().numpy()
+    want_s = np.zeros((k, d)); np.add.at(want_s, got, Xc.astype(np.float64))
+    np.testing.assert_allclose(sums, want_s, rtol=1e-12, atol=1e-10)
+    C64 = np.zeros((k, d)); nz = np.bincount(got, minlength=k) > 0
+    C64[nz] = want_s[nz] / np.bincount(got, minlength=k)[nz][:, None]
+    sq, rt, far = K.cluster_dispersion(dev(Xc), labels, dev(C64), want_far=True)
+    d2 = ((Xc.astype(np.float64) - C64[got]) ** 2).sum(1)
+    np.testing.assert_allclose(sq.cpu().numpy(), np.bincount(got, weights=d2, minlength=k), rtol=1e-11)
+    np.testing.assert_allclose(rt.cpu().numpy(), np.bincount(got, weights=np.sqrt(d2), minlength=k), rtol=1e-11)
+    np.testing.assert_allclose(far.cpu().numpy(), d2.astype(np.float32), rtol=1e-6)
+    C_new, C64d, stats = K.lloyd_update(dev(want_s), counts, nch, dev(C))
+    st = stats.cpu().numpy()
+    np.testing.assert_allclose(C_new.cpu().numpy()[nz], C64[nz].astype(np.float32), rtol=1e-6, atol=1e-9)
+    assert np.array_equal(st[2:], np.bincount(got, minlength=k).astype(np.float64)) and st[1] == 0
+
+
+@pytest.mark.parametrize('N,d,R,thr', [(2000, 512, 32, 0.55), (777, 768, 5, 0.9), (100, 1024, 40, -1.0), (64, 64, 1, 0.3)])
+def test_classify_kernel(K, N, d, R, thr):
+    B = blobs(N + R, d, kc=8, seed=0)
+    X, Rf = np.ascontiguousarray(B[:N]), np.ascontiguousarray(B[N:])
+    wdist, wlab = RC.classify_core(X, Rf, R, thr)
+    dist, lab = K.cosine_classify(K.normalize_rows(dev(X)), K.normalize_rows(dev(Rf)), thr)
+    assert np.array_equal(lab.cpu().numpy(), wlab)            # identical labels (north_star)
+    np.testing.assert_allclose(dist.cpu().numpy(), wdist, rtol=1e-5, atol=3e-7)
+
+
+@pytest.mark.parametrize('N,d,thr', [(1500, 512, 0.2), (700, 768, 0.25), (65, 1024, 0.2), (2, 512, 0.2), (1, 512, 0.2)])
+def test_dedup_kernel(engine, N, d, thr):
+    X = plant_dupes(blobs(N, d, kc=4, seed=5, normalize=(d == 512)), frac=20, seed=1, normalize=(d == 512))[0]
+    mins, inds, idx = engine.dedup(X, thr)
+    rmins, rinds, ridx = RC.dedup_core(X, thr)
+    ties = np.abs(rmins - np.float32(thr)) <= 1e-6
+    assert np.array_equal(np.setdiff1d(idx, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
+    if ties.any():
+        print('threshold ties at rows', np.nonzero(ties)[0])
+    np.testing.assert_allclose(mins, rmins, rtol=1e-4, atol=3e-7)
+    assert (inds == rinds).mean() > 0.99 and inds[0] == 0 and mins[0] == np.float32(10000.0)
+
+
+@pytest.mark.parametrize('N,d,k', [(500, 512, 3), (1000, 768, 5), (130, 64, 2)])
+def test_silhouette_exact_kernel(engine, N, d, k):
+    X = blobs(N, d, kc=k, seed=3, normalize=(d == 512))
+    lab = RC.kmeans_fit(X, k, 0).labels_
+    ctx = engine.prepare(X)
+    got = engine.silhouette_scores(ctx, [dev(lab, torch.int32)], [k], force='exact')[0]
+    want = RC.cluster_scores(X, lab)[0]
+    assert abs(got - want) <= 1e-5 * abs(want) + 1e-8
+
+
+def _tc_cluster_sums(engine, Xc_t, labels_t, ks):
+    """Run pack + tcgen05 sweep and fold the per-cell sums into per-cluster sums [N, k] per labelling."""
+    K = engine.K
+    perm, chunk_cell, c2c, G, P = engine.build_cells(labels_t, ks)
+    amax = float(K.absmax(Xc_t).item())
+    scale = 2.0 ** math.floor(math.log2(4096.0 / amax))
+    Xh, sqn = K.sil_pack(Xc_t, perm, P, scale)
+    cellsum = K.zeros((G, P), torch.float32)
+    K.sil_sweep(Xh, sqn, scale, chunk_cell, G, 0, P // 128, cellsum)
+    torch.cuda.synchronize()
+    cs, pm = cellsum.cpu().numpy().astype(np.float64), perm.cpu().numpy()
+    out = []
+    for j, k in enumerate(ks):
+        S = np.zeros((Xc_t.shape[0], k))
+        m = c2c[j].cpu().numpy()
+        live = pm >= 0
+        for g in range(G):
+            S[pm[live], m[g]] += cs[g, live]
+        out.append(S)
+    return out
+
+
+@pytest.mark.parametrize('N,d,ks', [(300, 64, [2]), (1000, 128, [2, 3]), (2500, 512, [2, 3, 4, 5, 6]),
+                                    (1200, 768, [2, 4]), (900, 1024, [3]), (5000, 512, [2, 6])])
+def test_tensor_core_sweep_matches_exact_rowsums(engine, N, d, ks):
+    """The tcgen05 kernel against the fp64-computed per-row cluster sums of the oracle."""
+    X = blobs(N, d, kc=4, seed=9, normalize=(d == 512))
+    ctx = engine.prepare(X)
+    rng = np.random.default_rng(0)
+    labels = [rng.integers(0, k, N).astype(np.int32) for k in ks]
+    got = _tc_cluster_sums(engine, ctx.Xc, [dev(l) for l in labels], ks)
+    for S, lab, k in zip(got, labels, ks):
+        want = RS.silhouette_rowsums(X, lab, k).astype(np.float64)
+        # fp16 operands: each distance carries ~2^-12 relative rounding noise, sums average it out
+        np.testing.assert_allclose(S, want, rtol=2e-4, atol=1e-3)
+        rel = np.abs(S.sum(0) - want.sum(0)) / want.sum(0)
+        assert rel.max() < 2e-5, rel                              # no systematic bias
+
+
+def test_sweep_rejects_bad_shapes(K):
+    from videotofaces_b200 import _native
+    with pytest.raises(_native.NativeError):
+        K.sil_sweep(torch.zeros((100, 64), dtype=torch.float16, device='cuda'), torch.zeros(100, device='cuda'), 1.0,
+                    torch.zeros(4, dtype=torch.int32, device='cuda'), 1, 0, 1, torch.zeros((1, 100), device='cuda'))

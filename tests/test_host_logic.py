@@ -1,0 +1,128 @@
+"""Host orchestration (engine.py) driven by the CPU stand-in kernels and checked against the
+scikit-learn oracle: k-means++ protocol and seed prefix sharing, the Lloyd loop and its stopping
+rules, empty-cluster relocation, the cell layout of the one-sweep silhouette, CH/DB, dedup key
+decoding, argument parsing.  CPU only -- the CUDA kernels themselves are checked by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+from fake_kernels import FakeKernels
+from oracle import reference_calls as RC
+from videotofaces_b200 import prep
+from videotofaces_b200.engine import GroupingEngine, n_local_trials, _ceil_to_f32
+from videotofaces_b200.dist import shard_bounds, cyclic_tiles
+from videotofaces_b200.synth import blobs, plant_dupes
+
+
+@pytest.fixture()
+def eng():
+    return GroupingEngine(FakeKernels())
+
+
+def test_kmeanspp_seeds_match_sklearn(eng):
+    X = blobs(3000, 512, kc=8, noise=1.0, seed=0)
+    ctx = eng.prepare(X)
+    for k in (2, 6):
+        assert np.array_equal(eng.kmeans_plusplus(ctx, k, 0), RC.kmeanspp_indices(X, k, 0))
+
+
+def test_seed_prefix_sharing(eng):
+    """Seeds of k are a prefix of k+1's while n_local_trials is equal."""
+    assert [n_local_trials(k) for k in (2, 3, 7, 8, 20, 21)] == [2, 3, 3, 4, 4, 5]
+    X = blobs(1500, 512, kc=8, noise=1.0, seed=3)
+    ctx = eng.prepare(X)
+    s7 = eng.kmeans_plusplus(ctx, 7, 5)
+    for k in (3, 5):
+        assert np.array_equal(RC.kmeanspp_indices(X, k, 5), s7[:k])
+
+
+@pytest.mark.parametrize('gen,ks', [
+    (lambda: blobs(2000, 512, kc=8, noise=1.0, seed=0), [2, 3, 4, 5, 6]),
+    (lambda: blobs(300, 768, kc=5, noise=1.0, seed=2, normalize=False), [2, 3, 4, 5]),
+])
+def test_sweep_matches_reference_calls(eng, gen, ks):
+    X = gen()
+    ctx, res = eng.kmeans_sweep(X, ks, 0)
+    ref = RC.cluster_core(X, ks, 0)
+    scores = eng.cluster_scores(ctx, res)
+    for r, lab, inertia, n_iter, sc, rsc in zip(res, ref['labels'], ref['inertia'], ref['n_iter'], scores, ref['scores']):
+        assert np.array_equal(r.labels.numpy(), lab)
+        assert r.n_iter == n_iter
+        np.testing.assert_allclose(r.inertia, inertia, rtol=1e-4)
+        np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-4)
+    assert max(scores, key=lambda s: s[1])[0] == ref['best_k']
+
+
+def test_cells_layout_and_tc_path_agree_with_exact(eng):
+    """build_cells: every 32-column chunk holds one cell, every row appears once; the cell-sum
+    silhouette (fp16 operands) equals the exact one within 1e-4."""
+    X = blobs(700, 128, kc=5, noise=1.0, seed=1)
+    ks = [2, 3, 5]
+    ctx, res = eng.kmeans_sweep(X, ks, 0)
+    labels = [r.labels for r in res]
+    perm, chunk_cell, c2c, G, P = eng.build_cells(labels, ks)
+    pm = perm.numpy()
+    assert P % 256 == 0 and sorted(pm[pm >= 0].tolist()) == list(range(700))
+    cc = np.repeat(chunk_cell.numpy(), 32)
+    for j, lab in enumerate(labels):
+        live = pm >= 0
+        assert np.array_equal(c2c[j].numpy()[cc[live]], lab.numpy()[pm[live]])
+    exact = eng.silhouette_scores(ctx, labels, ks, force='exact')
+    tc = eng.silhouette_scores(ctx, labels, ks, force='tc')
+    ref = [RC.cluster_scores(X, l.numpy())[0] for l in labels]
+    np.testing.assert_allclose(exact, ref, rtol=1e-5)
+    np.testing.assert_allclose(tc, ref, rtol=1e-4)
+
+
+def test_empty_cluster_relocation(eng):
+    """SK/cluster/tests/test_k_means.py:85-113: a centre that attracts nothing gets the farthest point."""
+    X = np.zeros((10, 4), dtype=np.float32)
+    X[:, 0] = [-10, -9.5, -9, -8.5, -8, -1, 1, 9, 9.5, 10]
+    init = np.zeros((3, 4), dtype=np.float32)
+    init[:, 0] = [-10, -10, -10]
+    ctx, res = eng.kmeans_sweep(X, [3], 0, inits=[init])
+    ref = RC.kmeans_fit(X, 3, 0, init=init)
+    assert np.unique(res[0].labels.numpy()).size == 3
+    np.testing.assert_allclose(res[0].inertia, ref.inertia_, rtol=1e-5)
+    assert np.array_equal(res[0].labels.numpy(), ref.labels_)
+
+
+def test_dedup_and_classify_decode(eng):
+    X = plant_dupes(blobs(400, 512, kc=4, noise=1.0, seed=0), frac=10, seed=1)[0]
+    mins, inds, idx = eng.dedup(X, 0.2)
+    rmins, rinds, ridx = RC.dedup_core(X, 0.2)
+    assert np.array_equal(idx, ridx) and mins[0] == np.float32(10000.0) and inds[0] == 0
+    np.testing.assert_allclose(mins, rmins, rtol=1e-5, atol=2e-7)
+    assert np.array_equal(eng.delete_rows(X, idx).numpy(), np.delete(X, idx, axis=0))
+    B = blobs(332, 512, kc=8, noise=1.0, seed=0)
+    for thr in (0.55, -1, None, 0):
+        dist, lab = eng.classify(B[:300], B[300:], thr)
+        _, rlab = RC.classify_core(B[:300], B[300:], 32, thr)
+        assert np.array_equal(lab, rlab)
+
+
+def test_four_rows_fail_like_the_reference(eng):
+    X = blobs(4, 512, kc=2, noise=0.5, seed=0)
+    ctx, res = eng.kmeans_sweep(X, [2, 3, 4], 0)
+    with pytest.raises(ValueError, match='Number of labels is 4'):
+        eng.cluster_scores(ctx, res)
+
+
+def test_ceil_to_f32_and_shards():
+    v = np.array([0.1, 1.0, 1e-9 + 1.0, 123456.789])
+    t = _ceil_to_f32(v)
+    assert (t.astype(np.float64) >= v).all() and (np.nextafter(t, np.float32(-np.inf)).astype(np.float64) < v).all()
+    assert shard_bounds(10, 3) == [0, 4, 7, 10]
+    assert shard_bounds(1000, 4, 64) == [0, 256, 512, 768, 1000]
+    assert shard_bounds(100, 4, 64) == [0, 64, 100, 100, 100]
+    assert cyclic_tiles(7, 1, 3) == [1, 4]
+
+
+def test_get_clusters_parsing(capsys):
+    """prep.py:48-66."""
+    assert prep.get_clusters(None) == list(range(2, 9))
+    assert prep.get_clusters('2-6') == [2, 3, 4, 5, 6]
+    assert prep.get_clusters('7,3,3,5') == [3, 5, 7]
+    assert prep.get_clusters(4) == [4]
+    assert prep.get_clusters('6-2') is None and prep.get_clusters('abc') is None
+    assert 'incorrent value for clusters' in capsys.readouterr().out

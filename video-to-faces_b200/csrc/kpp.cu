@@ -114,16 +114,34 @@ __global__ void __launch_bounds__(128) kpp_pick_kernel(const float* __restrict__
     for (int64_t c = 0; c < nchunks; ++c) {
         if (c + 1 < nchunks) load(c + 1);
         if (threadIdx.x == 0) {
-            const float* b = buf[c & 1];
+            // Distances are >= 0, so the running sum never decreases: test one prefix per 16 elements
+            // and replay the block element by element only when a threshold falls inside it.  The
+            // chunk is zero-padded past N (s + 0 == s), so whole blocks are always safe.
+            const float4* b4 = reinterpret_cast<const float4*>(buf[c & 1]);
             const int64_t base = c * kPickChunk;
-            const int n = (int)min((int64_t)kPickChunk, N - base);
-            for (int i = 0; i < n; ++i) {
-                s = __fadd_rn(s, b[i]);
-                while (s >= th) {      // searchsorted side='left': first i with cumsum[i] >= v
-                    idx[t] = base + i;
-                    ++t;
-                    th = t < T ? sthr[t] : INFINITY;
+#pragma unroll 2
+            for (int i = 0; i < kPickChunk / 4; i += 4) {
+                const float4 q0 = b4[i], q1 = b4[i + 1], q2 = b4[i + 2], q3 = b4[i + 3];
+                const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                                     q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                float e = s;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) e = __fadd_rn(e, v[j]);
+                if (e >= th) {
+                    float r = s;
+                    const float* bs = buf[c & 1] + 4 * i;   // re-read from shared: keeps v[] in registers
+#pragma unroll 1
+                    for (int j = 0; j < 16; ++j) {
+                        r = __fadd_rn(r, bs[j]);
+                        while (r >= th) {      // searchsorted side='left': first i with cumsum[i] >= v
+                            const int64_t g = base + 4 * i + j;
+                            idx[t] = g < N ? g : -1;
+                            ++t;
+                            th = t < T ? sthr[t] : INFINITY;
+                        }
+                    }
                 }
+                s = e;
             }
         }
         __syncthreads();

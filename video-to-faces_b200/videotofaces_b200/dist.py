@@ -62,10 +62,10 @@ def shard_bounds(n, world, align=1):
     """Contiguous shards of `n` units, each boundary a multiple of `align` (last one ragged)."""
     units = (n + align - 1) // align
     base, rem = divmod(units, world)
-    bounds = [0]
+    bounds, u = [0], 0
     for r in range(world):
-        bounds.append(min(n, (bounds[-1] // align + base + (1 if r < rem else 0)) * align))
-    bounds[-1] = n
+        u += base + (1 if r < rem else 0)
+        bounds.append(min(n, u * align))
     return bounds
 
 

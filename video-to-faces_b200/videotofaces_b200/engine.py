@@ -47,12 +47,38 @@ def _ceil_to_f32(v64):
     return t
 
 
+class _Span:
+    """CUDA-event bracket on the current stream (bench.py reads engine.events); a no-op unless
+    engine.profile is set."""
+
+    def __init__(self, eng, name, flops=0.0):
+        self.eng, self.name, self.flops = eng, name, flops
+        self.on = bool(eng.profile) and eng.device.type == 'cuda'
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            self.eng.events.append((self.name, self.a, self.b, self.flops))
+        return False
+
+
 class GroupingEngine:
     def __init__(self, kernels, comm=None):
         self.K = kernels
         self.comm = comm if comm is not None else Comm()
         self.device = kernels.device
-        self.timings = {}
+        self.profile = False
+        self.events = []
+
+    def span(self, name, flops=0.0):
+        return _Span(self, name, flops)
 
     # ------------------------------------------------------------------------------ utilities
     def to_device(self, A, dtype=torch.float32):
@@ -118,6 +144,10 @@ class GroupingEngine:
     # ------------------------------------------------------------------------------ a6 prologue
     def prepare(self, X):
         X = self.to_device(X)
+        with self.span('prepare'):
+            return self._prepare(X)
+
+    def _prepare(self, X):
         ctx = FitContext()
         ctx.X, ctx.N, ctx.d = X, X.shape[0], X.shape[1]
         ctx.bounds = self._bounds(ctx.N)
@@ -263,7 +293,8 @@ class GroupingEngine:
             for k in clusters:
                 by_trials.setdefault(n_local_trials(k), []).append(k)
             for trials, ks in by_trials.items():
-                seed_cache[trials] = self.kmeans_plusplus(ctx, max(ks), rstate)
+                with self.span('kmeans++'):
+                    seed_cache[trials] = self.kmeans_plusplus(ctx, max(ks), rstate)
         for j, k in enumerate(clusters):
             if inits is None:
                 seeds = seed_cache[n_local_trials(k)][:k]
@@ -271,7 +302,8 @@ class GroupingEngine:
             else:
                 seeds = None
                 C0 = (self.to_device(inits[j]) - ctx.mean32).contiguous()
-            res = self.lloyd(ctx, C0)
+            with self.span('lloyd'):
+                res = self.lloyd(ctx, C0)
             res.seeds = seeds
             results.append(res)
         return ctx, results
@@ -383,22 +415,26 @@ class GroupingEngine:
 
     def _silhouette_tc(self, ctx, labels_list, ks, counts_list):
         K, comm = self.K, self.comm
-        perm, chunk_cell, c2c, G, P = self.build_cells(labels_list, ks)
+        with self.span('sil_cells'):
+            perm, chunk_cell, c2c, G, P = self.build_cells(labels_list, ks)
         if G * P * 4 > TC_MAX_CELLSUM_BYTES and len(ks) > 1:
             h = len(ks) // 2                                                   # too many cells: sweep twice
             return (self._silhouette_tc(ctx, labels_list[:h], ks[:h], counts_list[:h]) +
                     self._silhouette_tc(ctx, labels_list[h:], ks[h:], counts_list[h:]))
         amax = float(K.absmax(ctx.Xc).item())
         scale = 1.0 if amax <= 0 else 2.0 ** math.floor(math.log2(4096.0 / amax))
-        Xh, sqn = K.sil_pack(ctx.Xc, perm, P, scale)
-        cellsum = K.zeros((G, P), torch.float32)
+        with self.span('sil_pack'):
+            Xh, sqn = K.sil_pack(ctx.Xc, perm, P, scale)
+            cellsum = K.zeros((G, P), torch.float32)
         bounds = self._bounds(P // 128, 1)
         rb0, rb1 = bounds[comm.rank], bounds[comm.rank + 1]
-        K.sil_sweep(Xh, sqn, scale, chunk_cell, G, rb0, rb1, cellsum)
+        with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * ctx.d):
+            K.sil_sweep(Xh, sqn, scale, chunk_cell, G, rb0, rb1, cellsum)
         out = K.zeros((len(ks),), torch.float64)
-        for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):
-            K.sil_finish_cells(cellsum, c2c[j], k, perm, lab, cnt, rb0 * 128, rb1 * 128, out[j:j + 1])
-        comm.allreduce_sum(out)
+        with self.span('sil_finish'):
+            for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):
+                K.sil_finish_cells(cellsum, c2c[j], k, perm, lab, cnt, rb0 * 128, rb1 * 128, out[j:j + 1])
+            comm.allreduce_sum(out)
         return (out / ctx.N).cpu().numpy().tolist()
 
     def cluster_scores(self, ctx, results, force=None):
@@ -408,7 +444,8 @@ class GroupingEngine:
         counts = [r.counts for r in results]
         sil = self.silhouette_scores(ctx, labels, ks, counts, force=force)
         out = []
-        for r, s in zip(results, sil):
-            ch, db = self.ch_db_scores(ctx, r.labels, r.k, r.counts)
-            out.append((r.k, float(s), ch, db))
+        with self.span('ch_db'):
+            for r, s in zip(results, sil):
+                ch, db = self.ch_db_scores(ctx, r.labels, r.k, r.counts)
+                out.append((r.k, float(s), ch, db))
         return out
