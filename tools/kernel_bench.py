@@ -1,0 +1,92 @@
+"""Per-kernel timings (CUDA events, after warm-up) against the HBM / tensor rooflines of MEASURED_PEAKS.json.
+
+    python tools/kernel_bench.py [--rows 1000000] [--dim 512] > gpurun_out/kernels.json
+"""
+import argparse
+import json
+import os.path as osp
+import sys
+
+ROOT = osp.dirname(osp.dirname(osp.abspath(__file__)))
+for p in (ROOT, osp.join(ROOT, 'video-to-faces_b200')):
+    sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--rows', type=int, default=1_000_000)
+    ap.add_argument('--dim', type=int, default=512)
+    ap.add_argument('--k', type=int, default=6)
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+    ge.build()
+    from videotofaces_b200.runtime import get_engine
+    eng = get_engine()
+    K = eng.K
+    N, d, k = args.rows, args.dim, args.k
+    try:
+        pk = json.load(open(osp.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # noqa: BLE001
+        pk = dict(hbm_gbs=6650.0, bf16_tflops_sustained=1400.0)
+    X = torch.randn(N, d, device='cuda')
+    X = X / X.norm(dim=1, keepdim=True)
+    mean = X.mean(0).contiguous()
+    C = X[torch.randint(0, N, (k,), device='cuda')].contiguous()
+    labels = torch.randint(0, k, (N,), device='cuda', dtype=torch.int32)
+    counts = torch.zeros(k, dtype=torch.int64, device='cuda')
+    nch = torch.zeros(1, dtype=torch.int64, device='cuda')
+    closest = torch.rand(N, device='cuda')
+    thr = torch.tensor([0.25, 0.5, 0.75], device='cuda') * float(closest.sum().item())
+    C64 = C.double()
+    R = X[:32].contiguous()
+    rows = []
+
+    def add(name, ms, nbytes=None, flops=None):
+        r = dict(kernel=name, ms=ms)
+        if nbytes:
+            r.update(gbs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / pk['hbm_gbs'], bytes=nbytes)
+        if flops:
+            r.update(tflops=flops / ms / 1e9, flop=flops)
+        rows.append(r)
+
+    B = N * d * 4
+    add('normalize_rows', timeit(lambda: K.normalize_rows(X)), 2 * B)
+    add('row_sqnorms', timeit(lambda: K.row_sqnorms(X)), B)
+    add('col_stats', timeit(lambda: K.col_stats(X)), B)
+    add('center_rows', timeit(lambda: K.center_rows(X, mean)), 2 * B)
+    add('kpp_dist T=3', timeit(lambda: K.kpp_dist(X, X[:3].contiguous(), closest)), B + 3 * N * 4 + N * 4)
+    add('kpp_pick (sequential fp32 chain)', timeit(lambda: K.kpp_pick(closest, thr)), N * 4)
+    add('lloyd_assign k=%d' % k, timeit(lambda: K.lloyd_assign(X, C, labels, counts, nch)), B + N * 8, 2.0 * N * k * d)
+    add('cluster_sums k=%d' % k, timeit(lambda: K.cluster_sums(X, labels, k)), B + N * 4)
+    add('cluster_dispersion k=%d' % k, timeit(lambda: K.cluster_dispersion(X, labels, C64)), B + N * 4)
+    add('cosine_classify R=32', timeit(lambda: K.cosine_classify(X, R, 0.9)), B + N * 32 * 4 + N * 8, 2.0 * N * 32 * d)
+    nd = min(N, 50_000)
+    Xd = X[:nd].contiguous()
+    add('cosine_dedup N=%d (fp32 FMA)' % nd, timeit(lambda: K.cosine_dedup(Xd, 0, 1), reps=3, warm=1), None, float(nd) * nd * d)
+    perm = torch.arange(N, device='cuda')
+    P = ((N + 255) // 256) * 256
+    perm = torch.cat([perm, torch.full((P - N,), -1, device='cuda', dtype=torch.int64)])
+    add('sil_pack', timeit(lambda: K.sil_pack(X, perm, P, 1024.0)), B + N * d * 2)
+    json.dump(dict(rows=args.rows, dim=d, peaks=dict(hbm_gbs=pk['hbm_gbs'], bf16_tflops_sustained=pk.get('bf16_tflops_sustained')),
+                   kernels=rows), sys.stdout, indent=1)
+    print()
+
+
+if __name__ == '__main__':
+    main()
