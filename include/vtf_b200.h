@@ -133,19 +133,22 @@ int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* strea
  * cell to a multiple of 32 columns, and the kernel accumulates, for each row, one distance
  * sum per cell.  See DESIGN.md for the layout.
  *
- * pack: Xh[p,:] = fp16(scale * X[perm[p],:]) for p < P (rows with perm[p] < 0 are zero
- * padding), sqn[p] = |Xh[p,:]|^2 / scale^2 computed from the ROUNDED values (so that the
- * distance is the exact distance between the rounded points), or -1e30 for padding so the
- * clamp at 0 removes them.  P % 256 == 0, d % 64 == 0.                                     */
+ * pack: Xh[p,:] = fp16(scale * X[perm[p],:]) for p < P (rows with perm[p] < 0 are zero padding) and the
+ * augmented operand aug = [A flavour | B flavour], each P*16 fp16 in UMMA no-swizzle K-major tile order:
+ * three fp16 pieces of m_p * 2^-shift (m_p = |Xh[p,:]|^2 / 2 from the ROUNDED values, so the distance is
+ * the exact distance between the rounded points) against the constant 2^shift, so that ONE extra K=16 MMA
+ * adds -m_p - m_q to the Gram accumulator.  Padding rows get m = -pad_m (pad_m >= 4 * max m), which clamps
+ * every distance to them to 0.  half_sqn[P] (nullable) receives m.  P % 256 == 0, d % 64 == 0.      */
 int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale,
-                 void* Xh, float* sqn, void* stream);
+                 int shift, float pad_m, void* Xh, void* aug, float* half_sqn, void* stream);
 /* out[0] = max |x| (picks the power-of-two fp16 scale).                                     */
 int vtf_absmax(const float* X, int64_t N, int d, float* out, void* stream);
-/* sweep: cellsum[g, p] += sum_{q in cell g} sqrt(max(sqn[p] + sqn[q] - 2 xh_p.xh_q / scale^2, 0))
+/* sweep: cellsum[g, p] += sum_{q in cell g} sqrt(max(2 (m_p + m_q - xh_p.xh_q), 0)) / scale
  * for row blocks [rb_begin, rb_end) of 128 rows, D_pp = 0.  chunk_cell[P/32] gives the cell
  * of every 32-column chunk.  cellsum is fp32 [n_cells, P], zeroed by the caller.
- * Requires sm_100a; d in {64..1024}, d % 64 == 0.                                          */
-int vtf_sil_sweep(const void* Xh, const float* sqn, int64_t P, int d, float scale,
+ * Requires sm_100a; d in {64..1024}, d % 64 == 0.  Even row-block ranges run as CTA pairs
+ * (cta_group::2); VTF_SWEEP_VARIANT=1 in the environment forces the single-CTA form.        */
+int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, float scale,
                   const int32_t* chunk_cell, int n_cells, int64_t rb_begin, int64_t rb_end,
                   float* cellsum, void* stream);
 /* finish: for labelling l (k_l clusters), per real row: a = S_own/(n_own-1),

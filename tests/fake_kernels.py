@@ -145,26 +145,29 @@ class FakeKernels:
     def absmax(self, X):
         return X.abs().max().reshape(1).to(torch.float32)
 
-    def sil_pack(self, X, perm, P, scale):
+    def sil_pack(self, X, perm, P, scale, shift, pad_m):
+        """aug stands in for the augmented operand: the half squared norms m of the ROUNDED rows."""
+        assert 0 <= shift <= 15 and pad_m * 2.0 ** -shift <= 32768.0
         x = _np(X)
         pm = _np(perm)
         xh = np.zeros((P, x.shape[1]), dtype=np.float16)
         live = pm >= 0
         xh[live] = (x[pm[live]] * np.float32(scale)).astype(np.float16)
         f = xh.astype(np.float32)
-        sqn = np.full(P, -1e30, dtype=np.float32)
-        sqn[live] = ((f[live] * f[live]).sum(1) / np.float32(scale * scale)).astype(np.float32)
-        return torch.from_numpy(xh), torch.from_numpy(sqn)
+        m = np.full(P, -pad_m, dtype=np.float32)
+        m[live] = 0.5 * (f[live] * f[live]).sum(1)
+        assert m.max() * 4 <= pad_m
+        return torch.from_numpy(xh), torch.from_numpy(m)
 
-    def sil_sweep(self, Xh, sqn, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
+    def sil_sweep(self, Xh, aug, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
         f = _np(Xh).astype(np.float32)
-        n = _np(sqn)
+        m = _np(aug)
         cc = np.repeat(_np(chunk_cell), 32)
         rows = np.arange(rb_begin * 128, rb_end * 128)
         if rows.size == 0:
             return
-        g = (f[rows] @ f.T) * np.float32(-2.0 / (scale * scale))
-        D = np.sqrt(np.maximum(g + n[rows][:, None] + n[None, :], 0)).astype(np.float32)
+        T = f[rows] @ f.T - m[rows][:, None] - m[None, :]
+        D = (np.sqrt(np.maximum(-T, 0)) * np.float32(np.sqrt(2.0) / scale)).astype(np.float32)
         D[np.arange(rows.size), rows] = 0
         for c in range(n_cells):
             cellsum[c, rows[0]:rows[-1] + 1] += torch.from_numpy(D[:, cc == c].sum(1, dtype=np.float32))

@@ -149,11 +149,10 @@ def _tc_cluster_sums(engine, Xc_t, labels_t, ks):
     """Run pack + tcgen05 sweep and fold the per-cell sums into per-cluster sums [N, k] per labelling."""
     K = engine.K
     perm, chunk_cell, c2c, G, P = engine.build_cells(labels_t, ks)
-    amax = float(K.absmax(Xc_t).item())
-    scale = 2.0 ** math.floor(math.log2(4096.0 / amax))
-    Xh, sqn = K.sil_pack(Xc_t, perm, P, scale)
+    scale, shift, pad_m = engine.sil_scale(Xc_t)
+    Xh, aug = K.sil_pack(Xc_t, perm, P, scale, shift, pad_m)
     cellsum = K.zeros((G, P), torch.float32)
-    K.sil_sweep(Xh, sqn, scale, chunk_cell, G, 0, P // 128, cellsum)
+    K.sil_sweep(Xh, aug, scale, chunk_cell, G, 0, P // 128, cellsum)
     torch.cuda.synchronize()
     cs, pm = cellsum.cpu().numpy().astype(np.float64), perm.cpu().numpy()
     out = []
@@ -187,5 +186,5 @@ def test_tensor_core_sweep_matches_exact_rowsums(engine, N, d, ks):
 def test_sweep_rejects_bad_shapes(K):
     from videotofaces_b200 import _native
     with pytest.raises(_native.NativeError):
-        K.sil_sweep(torch.zeros((100, 64), dtype=torch.float16, device='cuda'), torch.zeros(100, device='cuda'), 1.0,
+        K.sil_sweep(torch.zeros((100, 64), dtype=torch.float16, device='cuda'), torch.zeros((2, 100, 16), dtype=torch.float16, device='cuda'), 1.0,
                     torch.zeros(4, dtype=torch.int32, device='cuda'), 1, 0, 1, torch.zeros((1, 100), device='cuda'))

@@ -82,7 +82,7 @@ def main():
     perm = torch.arange(N, device='cuda')
     P = ((N + 255) // 256) * 256
     perm = torch.cat([perm, torch.full((P - N,), -1, device='cuda', dtype=torch.int64)])
-    add('sil_pack', timeit(lambda: K.sil_pack(X, perm, P, 1024.0)), B + N * d * 2)
+    add('sil_pack', timeit(lambda: K.sil_pack(X, perm, P, 1024.0, 6, 4.0 * 0.5 * 1024.0 ** 2 * 1.02)), B + N * d * 2)
     json.dump(dict(rows=args.rows, dim=d, peaks=dict(hbm_gbs=pk['hbm_gbs'], bf16_tflops_sustained=pk.get('bf16_tflops_sustained')),
                    kernels=rows), sys.stdout, indent=1)
     print()

@@ -20,6 +20,7 @@
 // accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
 // MMAs of tile t+1.  Algorithmic flops 2*P^2*d per sweep; tensor-bound.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vtf {
@@ -35,7 +36,6 @@ constexpr int kBBlockBytes = BN * BK * 2;   // 32 KB
 constexpr unsigned long long kTimeoutCycles = 6000000000ull;   // ~3 s: trap instead of hanging the GPU
 
 struct Params {
-    const float* sqn;
     const int32_t* chunk_cell;
     float* cellsum;
     int64_t P;
@@ -45,7 +45,7 @@ struct Params {
     int n_seg;           // column segments per row block
     int tiles_per_seg;   // 256-column tiles per segment
     int n_tiles;         // P / 256
-    float neg2_inv_s2;   // -2 / scale^2
+    float flush_scale;   // sqrt(2) / scale: sqrt(max(-T, 0)) * flush_scale is the distance
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,6 +79,42 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) flavours: the pair shares one 256-row MMA, each CTA feeds half of B
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // cute::Sm100MmaPeerBitMask: address of the same barrier in the even CTA
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -101,8 +137,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// The augmented 16-column block is stored in the canonical NO-swizzle K-major order (silhouette.cu, store_aug):
+// core matrix = 8 rows x 16 B contiguous, the two K core matrices 128 B apart (LBO), 8-row groups 256 B apart (SBO).
+__device__ __forceinline__ uint64_t make_desc_aug(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 over two CTAs
 
 #define VTF_TMEM_LD32(taddr, v)                                                                              \
     asm volatile(                                                                                            \
@@ -132,13 +175,26 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 // A_RESIDENT: the item's 128 x d A block is loaded once and kept; otherwise A k-blocks stream with B.
-template <bool A_RESIDENT, int STAGES>
+// PAIR: two CTAs of a cluster (one SM pair) run one cta_group::2 MMA of 256 rows x 256 columns: each
+// CTA keeps its own 128-row A block and streams only HALF of every B tile, which halves the L2->SM
+// traffic (the limiter of the single-CTA form: 64 B/cycle/SM against ~42 B/cycle/SM of L2 bandwidth)
+// and the shared-memory write traffic.  CTA 0 issues the MMAs; barriers that both CTAs wait on are
+// signalled with multicast commits, the accumulator-drained barrier collects arrivals from both.
+template <bool A_RESIDENT, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params prm) {
+sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_aug_a, const __grid_constant__ CUtensorMap map_aug_b, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte swizzle needs 1024-byte aligned tiles
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    constexpr int kStageBytes = kBBlockBytes + (A_RESIDENT ? 0 : kABlockBytes);
+    constexpr int CPC = PAIR ? 2 : 1;                        // CTAs per work unit
+    constexpr int kBBytes = kBBlockBytes / CPC;              // B bytes this CTA loads per k-block
+    constexpr int kStageBytes = kBBytes + (A_RESIDENT ? 0 : kABlockBytes);
+    constexpr int kAugABytes = BM * 32;                      // 128 rows x 16 fp16
+    constexpr int kAugBBytes = (BN / CPC) * 32;              // this CTA's B rows x 16 fp16
+    static_assert(kAugABytes + kAugBBytes <= kStageBytes, "the augmented block travels in a ring slot");
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     const uint32_t a_res = base;                                                  // [n_kb][16 KB] when resident
     const uint32_t stage0 = base + (A_RESIDENT ? (uint32_t)prm.n_kb * kABlockBytes : 0u);
     const uint32_t bars = stage0 + STAGES * kStageBytes;
@@ -157,57 +213,85 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * CPC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int64_t n_items = prm.n_rb * prm.n_seg;
+    const int64_t n_items = (prm.n_rb / CPC) * prm.n_seg;     // work units: row block (pair) x column segment
+    const int64_t unit0 = blockIdx.x / CPC, unit_stride = gridDim.x / CPC;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, a_ph = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int64_t rb = prm.rb_begin + item / prm.n_seg;
+            for (int64_t item = unit0; item < n_items; item += unit_stride) {
+                const int64_t rb = prm.rb_begin + CPC * (item / prm.n_seg) + cta_rank;
                 const int seg = (int)(item % prm.n_seg);
                 const int t0 = seg * prm.tiles_per_seg;
                 const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+                // PAIR: both CTAs load; every complete_tx lands on the LEADER's barrier, which expects both halves
                 if (A_RESIDENT) {
                     mbar_wait(a_empty, a_ph ^ 1u);
-                    mbar_expect_tx(a_full, (uint32_t)prm.n_kb * kABlockBytes);
-                    for (int kb = 0; kb < prm.n_kb; ++kb)
-                        tma_load_2d(&map_a, a_full, a_res + (uint32_t)kb * kABlockBytes, kb * BK, (int)(rb * BM));
+                    if (leader) mbar_expect_tx(a_full, (uint32_t)prm.n_kb * kABlockBytes * CPC);
+                    for (int kb = 0; kb < prm.n_kb; ++kb) {
+                        if (PAIR) tma_load_2d_pair(&map_a, a_full, a_res + (uint32_t)kb * kABlockBytes, kb * BK, (int)(rb * BM));
+                        else tma_load_2d(&map_a, a_full, a_res + (uint32_t)kb * kABlockBytes, kb * BK, (int)(rb * BM));
+                    }
                     a_ph ^= 1u;
                 }
                 for (int t = t0; t < t1; ++t) {
                     for (int kb = 0; kb < prm.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1u);
-                        mbar_expect_tx(full_bar(s), (uint32_t)kStageBytes);
+                        if (leader) mbar_expect_tx(full_bar(s), (uint32_t)kStageBytes * CPC);
                         const uint32_t dst = stage0 + (uint32_t)s * kStageBytes;
-                        tma_load_2d(&map_b, full_bar(s), dst, kb * BK, t * BN);
-                        if (!A_RESIDENT) tma_load_2d(&map_a, full_bar(s), dst + kBBlockBytes, kb * BK, (int)(rb * BM));
+                        if (PAIR) {
+                            // this CTA's half of the 256 B rows: [t*256 + rank*128, +128)
+                            tma_load_2d_pair(&map_b, full_bar(s), dst, kb * BK, t * BN + (int)cta_rank * (BN / 2));
+                            if (!A_RESIDENT) tma_load_2d_pair(&map_a, full_bar(s), dst + kBBytes, kb * BK, (int)(rb * BM));
+                        } else {
+                            tma_load_2d(&map_b, full_bar(s), dst, kb * BK, t * BN);
+                            if (!A_RESIDENT) tma_load_2d(&map_a, full_bar(s), dst + kBBytes, kb * BK, (int)(rb * BM));
+                        }
                         if (++s == STAGES) { s = 0; ph ^= 1u; }
                     }
+                    // one more ring slot per tile: the augmented K=16 block (norm terms) of B and of A
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (leader) mbar_expect_tx(full_bar(s), (uint32_t)(kAugABytes + kAugBBytes) * CPC);
+                    const uint32_t dst = stage0 + (uint32_t)s * kStageBytes;
+                    const int bgrp = (t * BN + (int)cta_rank * (BN / CPC)) / 8;      // 8-row groups of 256 B
+                    if (PAIR) {
+                        tma_load_2d_pair(&map_aug_b, full_bar(s), dst, 0, bgrp);
+                        tma_load_2d_pair(&map_aug_a, full_bar(s), dst + kAugBBytes, 0, (int)(rb * BM / 8));
+                    } else {
+                        tma_load_2d(&map_aug_b, full_bar(s), dst, 0, bgrp);
+                        tma_load_2d(&map_aug_a, full_bar(s), dst + kAugBBytes, 0, (int)(rb * BM / 8));
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
             int s = 0, as = 0;
             uint32_t ph = 0, a_ph = 0, acc_ph = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int64_t item = unit0; item < n_items; item += unit_stride) {
                 const int seg = (int)(item % prm.n_seg);
                 const int t0 = seg * prm.tiles_per_seg;
                 const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
@@ -220,21 +304,36 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         mbar_wait(full_bar(s), ph);
                         tc_fence_after();
                         const uint32_t b_addr = stage0 + (uint32_t)s * kStageBytes;
-                        const uint32_t a_addr = A_RESIDENT ? a_res + (uint32_t)kb * kABlockBytes : b_addr + kBBlockBytes;
+                        const uint32_t a_addr = A_RESIDENT ? a_res + (uint32_t)kb * kABlockBytes : b_addr + kBBytes;
                         const uint64_t a_desc = make_desc(a_addr), b_desc = make_desc(b_addr);
 #pragma unroll
                         for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row: start field += 2
-                            tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k4), b_desc + (uint64_t)(2 * k4), kIdesc,
-                                       (uint32_t)((kb | k4) != 0));
+                            if (PAIR) tc_mma_f16_pair(d_tmem, a_desc + (uint64_t)(2 * k4), b_desc + (uint64_t)(2 * k4), kIdescPair,
+                                                      (uint32_t)((kb | k4) != 0));
+                            else tc_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k4), b_desc + (uint64_t)(2 * k4), kIdesc,
+                                            (uint32_t)((kb | k4) != 0));
                         }
-                        tc_commit(empty_bar(s));   // frees the smem stage once these MMAs retire
+                        // frees the smem stage (in both CTAs) once these MMAs retire
+                        if (PAIR) tc_commit_pair(empty_bar(s)); else tc_commit(empty_bar(s));
                         if (++s == STAGES) { s = 0; ph ^= 1u; }
                     }
-                    tc_commit(tfull_bar(as));       // accumulator complete -> epilogue
+                    {   // T = G' - m_p - m_q: one K=16 MMA over the augmented block finishes the accumulator
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint32_t b_addr = stage0 + (uint32_t)s * kStageBytes;
+                        const uint64_t a_desc = make_desc_aug(b_addr + kAugBBytes), b_desc = make_desc_aug(b_addr);
+                        if (PAIR) tc_mma_f16_pair(d_tmem, a_desc, b_desc, kIdescPair, 1u);
+                        else tc_mma_f16(d_tmem, a_desc, b_desc, kIdesc, 1u);
+                        if (PAIR) tc_commit_pair(empty_bar(s)); else tc_commit(empty_bar(s));
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    }
+                    // accumulator complete -> epilogue warps of both CTAs
+                    if (PAIR) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as));
                     if (++as == 2) { as = 0; acc_ph ^= 1u; }
                 }
-                if (A_RESIDENT) tc_commit(a_empty); // A block may be overwritten for the next item
+                // A block may be overwritten for the next item
+                if (A_RESIDENT) { if (PAIR) tc_commit_pair(a_empty); else tc_commit(a_empty); }
             }
         }
         __syncwarp();
@@ -244,14 +343,13 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int half = (warp - 2) >> 2;       // which 128 columns of the 256-wide tile
         int as = 0;
         uint32_t acc_ph = 0;
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int64_t rb = prm.rb_begin + item / prm.n_seg;
+        for (int64_t item = unit0; item < n_items; item += unit_stride) {
+            const int64_t rb = prm.rb_begin + CPC * (item / prm.n_seg) + cta_rank;
             const int seg = (int)(item % prm.n_seg);
             const int t0 = seg * prm.tiles_per_seg;
             const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
             const int64_t rowbase = rb * BM + q * 32;
             const int64_t p = rowbase + lane;
-            const float ni = __ldg(prm.sqn + p);
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             int cur_cell = -1;
             for (int t = t0; t < t1; ++t) {
@@ -265,42 +363,45 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     VTF_TMEM_LD32(taddr, v);
                     const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
                     if (cell != cur_cell) {
-                        if (cur_cell >= 0) atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, (acc0 + acc1) + (acc2 + acc3));
+                        if (cur_cell >= 0)
+                            atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);
                         acc0 = acc1 = acc2 = acc3 = 0.f;
                         cur_cell = cell;
                     }
-                    const float4* nj4 = reinterpret_cast<const float4*>(prm.sqn + col0);
                     VTF_TMEM_WAIT(v);
-                    const bool diag = (col0 == rowbase);
+                    // the accumulator holds T = s^2 (x_p.x_q - |x_p|^2/2 - |x_q|^2/2) = -s^2 D^2 / 2:
+                    // distance = sqrt(max(-T, 0)) * sqrt(2)/s, the constant factor applied once per flush
+                    if (col0 != rowbase) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 nj = __ldg(nj4 + j4);
-                        float r0 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), prm.neg2_inv_s2, ni + nj.x), 0.f));
-                        float r1 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), prm.neg2_inv_s2, ni + nj.y), 0.f));
-                        float r2 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), prm.neg2_inv_s2, ni + nj.z), 0.f));
-                        float r3 = sqrt_approx(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), prm.neg2_inv_s2, ni + nj.w), 0.f));
-                        if (diag) {   // D_pp = 0 (SK/metrics/pairwise.py:2285)
-                            if (lane == 4 * j4 + 0) r0 = 0.f;
-                            if (lane == 4 * j4 + 1) r1 = 0.f;
-                            if (lane == 4 * j4 + 2) r2 = 0.f;
-                            if (lane == 4 * j4 + 3) r3 = 0.f;
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            acc0 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 0]), 0.f));
+                            acc1 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 1]), 0.f));
+                            acc2 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 2]), 0.f));
+                            acc3 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 3]), 0.f));
                         }
-                        acc0 += r0; acc1 += r1; acc2 += r2; acc3 += r3;
+                    } else {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float r = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
+                            acc0 += (j == lane) ? 0.f : r;
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(as));
+                if (lane == 0) { if (PAIR) mbar_arrive_remote(tempty_bar(as), 0u); else mbar_arrive(tempty_bar(as)); }
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
-            if (cur_cell >= 0) atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, (acc0 + acc1) + (acc2 + acc3));
+            if (cur_cell >= 0)
+                atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's shared memory until the end
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -321,6 +422,25 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// aug: [P/8 groups][128 fp16 = 256 B], already in UMMA order; box = `groups` groups, no swizzle
+static int make_aug_map(CUtensorMap* map, const void* aug, int64_t P, int groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(VTF_ERR_CUDA, "vtf_sil_sweep", "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {128, (cuuint64_t)(P / 8)};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {128, (cuuint32_t)groups};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(aug), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(aug) failed (%d)", (int)r);
+        return fail(VTF_ERR_CUDA, "vtf_sil_sweep", buf);
+    }
+    return VTF_OK;
+}
+
 static int make_map(CUtensorMap* map, const void* Xh, int64_t P, int d, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(VTF_ERR_CUDA, "vtf_sil_sweep", "cuTensorMapEncodeTiled unavailable");
@@ -339,13 +459,27 @@ static int make_map(CUtensorMap* map, const void* Xh, int64_t P, int d, int box_
     return VTF_OK;
 }
 
-template <bool A_RES, int STAGES>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& prm, int grid, void* stream) {
-    const size_t stage = kBBlockBytes + (A_RES ? 0 : kABlockBytes);
+template <bool A_RES, int STAGES, bool PAIR>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& maa, const CUtensorMap& mab,
+                  const Params& prm, int grid, void* stream) {
+    const size_t stage = kBBlockBytes / (PAIR ? 2 : 1) + (A_RES ? 0 : kABlockBytes);
     const size_t smem = 1024 + (A_RES ? (size_t)prm.n_kb * kABlockBytes : 0) + STAGES * stage + 256;
-    VTF_CUDA(cudaFuncSetAttribute(sil_sweep_kernel<A_RES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-             "vtf_sil_sweep/smem");
-    VTF_LAUNCH((sil_sweep_kernel<A_RES, STAGES>), grid, kThreads, smem, stream, ma, mb, prm);
+    auto kern = sil_sweep_kernel<A_RES, STAGES, PAIR>;
+    VTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "vtf_sil_sweep/smem");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VTF_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, maa, mab, prm), "vtf_sil_sweep/launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     VTF_CHECK_LAST("vtf_sil_sweep");
     return VTF_OK;
 }
@@ -355,30 +489,47 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& pr
 
 using namespace vtf;
 
-extern "C" int vtf_sil_sweep(const void* Xh, const float* sqn, int64_t P, int d, float scale, const int32_t* chunk_cell,
+extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, float scale, const int32_t* chunk_cell,
                              int n_cells, int64_t rb_begin, int64_t rb_end, float* cellsum, void* stream) {
-    VTF_REQUIRE(Xh && sqn && chunk_cell && cellsum && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0 &&
+    VTF_REQUIRE(Xh && aug && chunk_cell && cellsum && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0 &&
                     n_cells > 0 && rb_begin >= 0 && rb_end <= P / tc::BM && scale > 0.f,
                 "vtf_sil_sweep (P % 256 == 0, d % 64 == 0, 64 <= d <= 1024)");
     if (rb_end <= rb_begin) return VTF_OK;
     int rc = vtf_device_check();
     if (rc != VTF_OK) return rc;
-    CUtensorMap ma, mb;
+    // variant: 2 = CTA pairs (cta_group::2, default when the row-block count is even), 1 = single CTA
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("VTF_SWEEP_VARIANT"); forced = e ? atoi(e) : 0; }
+    const bool even = ((rb_end - rb_begin) % 2 == 0) && (rb_begin % 2 == 0);
+    const bool pair = even && forced != 1;
+    CUtensorMap ma, mb, maa, mab;
     if ((rc = tc::make_map(&ma, Xh, P, d, tc::BM)) != VTF_OK) return rc;
-    if ((rc = tc::make_map(&mb, Xh, P, d, tc::BN)) != VTF_OK) return rc;
+    if ((rc = tc::make_map(&mb, Xh, P, d, pair ? tc::BN / 2 : tc::BN)) != VTF_OK) return rc;
+    const __half* augA = (const __half*)aug;
+    const __half* augB = augA + (size_t)P * 16;
+    if ((rc = tc::make_aug_map(&maa, augA, P, tc::BM / 8)) != VTF_OK) return rc;
+    if ((rc = tc::make_aug_map(&mab, augB, P, (pair ? tc::BN / 2 : tc::BN) / 8)) != VTF_OK) return rc;
     tc::Params prm;
-    prm.sqn = sqn; prm.chunk_cell = chunk_cell; prm.cellsum = cellsum; prm.P = P;
+    prm.chunk_cell = chunk_cell; prm.cellsum = cellsum; prm.P = P;
     prm.rb_begin = rb_begin; prm.n_rb = rb_end - rb_begin;
     prm.n_kb = d / tc::BK;
     prm.n_tiles = (int)(P / tc::BN);
     const int sms = num_sms();
-    // enough items to fill the machine twice when the row blocks alone cannot
+    const int64_t units = pair ? prm.n_rb / 2 : prm.n_rb;
+    const int64_t slots = pair ? sms / 2 : sms;
+    // enough work units to fill the machine twice when the row blocks alone cannot
     int n_seg = 1;
-    if (prm.n_rb < 2 * (int64_t)sms) n_seg = (int)min((int64_t)prm.n_tiles, (2 * (int64_t)sms + prm.n_rb - 1) / prm.n_rb);
+    if (units < 2 * slots) n_seg = (int)min((int64_t)prm.n_tiles, (2 * slots + units - 1) / units);
     prm.tiles_per_seg = (prm.n_tiles + n_seg - 1) / n_seg;
     prm.n_seg = (prm.n_tiles + prm.tiles_per_seg - 1) / prm.tiles_per_seg;
-    prm.neg2_inv_s2 = -2.f / (scale * scale);
-    const int grid = (int)min((int64_t)sms, prm.n_rb * prm.n_seg);
-    if (d <= 512) return tc::launch<true, 3>(ma, mb, prm, grid, stream);
-    return tc::launch<false, 4>(ma, mb, prm, grid, stream);
+    prm.flush_scale = 1.41421356237f / scale;
+    const int64_t n_units = units * prm.n_seg;
+    if (pair) {
+        const int grid = 2 * (int)min(slots, n_units);
+        if (d <= 512) return tc::launch<true, 6, true>(ma, mb, maa, mab, prm, grid, stream);
+        return tc::launch<false, 6, true>(ma, mb, maa, mab, prm, grid, stream);
+    }
+    const int grid = (int)min(slots, n_units);
+    if (d <= 512) return tc::launch<true, 3, false>(ma, mb, maa, mab, prm, grid, stream);
+    return tc::launch<false, 4, false>(ma, mb, maa, mab, prm, grid, stream);
 }

@@ -119,17 +119,21 @@ __global__ void __launch_bounds__(128) kpp_pick_kernel(const float* __restrict__
             // chunk is zero-padded past N (s + 0 == s), so whole blocks are always safe.
             const float4* b4 = reinterpret_cast<const float4*>(buf[c & 1]);
             const int64_t base = c * kPickChunk;
-#pragma unroll 2
+            // software pipeline: the 4 x LDS.128 of block i+1 are in flight while the 16-add chain of
+            // block i (the critical path: 16 x 4 cycles) runs
+            float4 n0 = b4[0], n1 = b4[1], n2 = b4[2], n3 = b4[3];
+#pragma unroll 1
             for (int i = 0; i < kPickChunk / 4; i += 4) {
-                const float4 q0 = b4[i], q1 = b4[i + 1], q2 = b4[i + 2], q3 = b4[i + 3];
-                const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
-                                     q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                const float4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+                if (i + 4 < kPickChunk / 4) { n0 = b4[i + 4]; n1 = b4[i + 5]; n2 = b4[i + 6]; n3 = b4[i + 7]; }
                 float e = s;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) e = __fadd_rn(e, v[j]);
+                e = __fadd_rn(e, q0.x); e = __fadd_rn(e, q0.y); e = __fadd_rn(e, q0.z); e = __fadd_rn(e, q0.w);
+                e = __fadd_rn(e, q1.x); e = __fadd_rn(e, q1.y); e = __fadd_rn(e, q1.z); e = __fadd_rn(e, q1.w);
+                e = __fadd_rn(e, q2.x); e = __fadd_rn(e, q2.y); e = __fadd_rn(e, q2.z); e = __fadd_rn(e, q2.w);
+                e = __fadd_rn(e, q3.x); e = __fadd_rn(e, q3.y); e = __fadd_rn(e, q3.z); e = __fadd_rn(e, q3.w);
                 if (e >= th) {
                     float r = s;
-                    const float* bs = buf[c & 1] + 4 * i;   // re-read from shared: keeps v[] in registers
+                    const float* bs = buf[c & 1] + 4 * i;   // rare: replay the block element by element
 #pragma unroll 1
                     for (int j = 0; j < 16; ++j) {
                         r = __fadd_rn(r, bs[j]);

@@ -8,13 +8,38 @@
 
 namespace vtf {
 
-// warp per output row p: Xh[p,:] = fp16_rn(scale * X[perm[p],:]); sqn[p] = |Xh[p,:]|^2 / scale^2
+// Augmented operand ("the norms ride in the MMA"): 16 extra fp16 K-columns per row so that one more
+// K=16 tcgen05.mma adds -m_p - m_q (m = |h|^2 / 2) to the Gram accumulator:
+//   A flavour  [-m_hi, -m_mid, -m_lo,  C,  C,  C, 0 x 10]      B flavour  [C, C, C, -m_hi, -m_mid, -m_lo, 0 x 10]
+// with m' = m * 2^-shift split into three fp16 pieces (33 bits >= fp32's 24) and C = 2^shift.
+// Stored in the canonical no-swizzle K-major UMMA order so a plain tiled TMA copy lands it ready to use:
+// element (p, k) at byte (p/8)*256 + (k/8)*128 + (p%8)*16 + (k%8)*2.
+__device__ __forceinline__ void store_aug(__half* augA, __half* augB, int64_t p, float v, float cpow) {
+    const __half hi = __float2half_rn(v);
+    const float r1 = v - __half2float(hi);
+    const __half mid = __float2half_rn(r1);
+    const __half lo = __float2half_rn(r1 - __half2float(mid));
+    const __half c = __float2half_rn(cpow), z = __float2half_rn(0.f);
+    const __half nh = __hneg(hi), nm = __hneg(mid), nl = __hneg(lo);
+    const size_t off = (size_t)(p >> 3) * 128 + (size_t)(p & 7) * 8;     // in halfs
+    __half a0[8] = {nh, nm, nl, c, c, c, z, z};
+    __half b0[8] = {c, c, c, nh, nm, nl, z, z};
+    *reinterpret_cast<uint4*>(augA + off) = *reinterpret_cast<const uint4*>(a0);
+    *reinterpret_cast<uint4*>(augB + off) = *reinterpret_cast<const uint4*>(b0);
+    *reinterpret_cast<uint4*>(augA + off + 64) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(augB + off + 64) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// warp per output row p: Xh[p,:] = fp16_rn(scale * X[perm[p],:]); m_p = |Xh[p,:]|^2 / 2 computed from the
+// ROUNDED values, so the distance is the exact distance between the rounded points.  Padding rows are zero
+// vectors with m = -pad_m (a large negative half-norm): every distance to them clamps to 0.
 __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__ X, int64_t N, int d,
                                                        const int64_t* __restrict__ perm, int64_t P, float scale,
-                                                       __half* __restrict__ Xh, float* __restrict__ sqn) {
+                                                       float inv_pow, float cpow, float pad_m,
+                                                       __half* __restrict__ Xh, __half* __restrict__ augA,
+                                                       __half* __restrict__ augB, float* __restrict__ half_sqn) {
     const int lane = threadIdx.x & 31;
     const int nvec = d >> 2;
-    const float inv_s2 = 1.f / (scale * scale);
     int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (; p < P; p += stride) {
@@ -22,7 +47,10 @@ __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__
         uint2* out = reinterpret_cast<uint2*>(Xh + p * d);
         if (src < 0) {
             for (int v = lane; v < nvec; v += 32) out[v] = make_uint2(0u, 0u);
-            if (lane == 0) sqn[p] = -1e30f;     // clamp at 0 removes padded columns from every sum
+            if (lane == 0) {
+                store_aug(augA, augB, p, -pad_m * inv_pow, cpow);
+                if (half_sqn) half_sqn[p] = -pad_m;
+            }
             continue;
         }
         const float4* xr = reinterpret_cast<const float4*>(X + src * d);
@@ -40,7 +68,11 @@ __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__
             out[v] = o;
         }
         s = warp_sum(s);
-        if (lane == 0) sqn[p] = s * inv_s2;
+        if (lane == 0) {
+            const float m = 0.5f * s;
+            store_aug(augA, augB, p, m * inv_pow, cpow);
+            if (half_sqn) half_sqn[p] = m;
+        }
     }
 }
 
@@ -149,12 +181,18 @@ int vtf_absmax(const float* X, int64_t N, int d, float* out, void* stream) {
     return VTF_OK;
 }
 
-int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale, void* Xh, float* sqn,
-                 void* stream) {
-    VTF_REQUIRE(X && Xh && sqn && N >= 0 && P >= 0 && d > 0 && d % 4 == 0 && scale > 0.f, "vtf_sil_pack");
+int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale, int shift, float pad_m,
+                 void* Xh, void* aug, float* half_sqn, void* stream) {
+    VTF_REQUIRE(X && Xh && aug && N >= 0 && P >= 0 && P % 8 == 0 && d > 0 && d % 4 == 0 && scale > 0.f && shift >= 0 &&
+                    shift <= 15 && pad_m > 0.f,
+                "vtf_sil_pack");
     if (P == 0) return VTF_OK;
     const int grid = (int)min((int64_t)num_sms() * 8, (P + 7) / 8);
-    VTF_LAUNCH(sil_pack_kernel, grid, 256, 0, stream, X, N, d, perm, P, scale, (__half*)Xh, sqn);
+    const float cpow = (float)(1 << shift);
+    __half* augA = (__half*)aug;
+    __half* augB = augA + (size_t)P * 16;
+    VTF_LAUNCH(sil_pack_kernel, grid, 256, 0, stream, X, N, d, perm, P, scale, 1.f / cpow, cpow, pad_m, (__half*)Xh, augA,
+               augB, half_sqn);
     VTF_CHECK_LAST("vtf_sil_pack");
     return VTF_OK;
 }

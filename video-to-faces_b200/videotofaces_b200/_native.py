@@ -35,7 +35,7 @@ SIGNATURES = {
     'vtf_gather_rows': (c_int, [c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
     'vtf_silhouette_rowsums_exact': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     'vtf_row_sqnorms': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
-    'vtf_sil_pack': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    'vtf_sil_pack': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'vtf_absmax': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_sil_sweep': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     'vtf_sil_finish_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),

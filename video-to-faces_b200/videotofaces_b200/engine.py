@@ -413,6 +413,21 @@ class GroupingEngine:
         c2c = torch.stack([lab[rep].to(torch.int32) for lab in labels_list]).contiguous()
         return perm, chunk_cell, c2c, G, P
 
+    def sil_scale(self, Xc):
+        """Power-of-two scale s for the fp16 operand and the split of the half squared norms m = s^2 |x|^2 / 2
+        that ride in the MMA as fp16 pieces m * 2^-shift against the constant 2^shift.
+        Constraints: max |x| s <= 4096 (fp16 keeps 11 significant bits), pad_m = 4 max(m) * 2^-shift <= 32768
+        with shift <= 15.  Returns (scale, shift, pad_m)."""
+        amax = float(self.K.absmax(Xc).item())
+        max_sqn = float(self.K.row_sqnorms(Xc).max().item())
+        if amax <= 0.0 or max_sqn <= 0.0:
+            return 1.0, 0, 1.0
+        scale = 2.0 ** math.floor(math.log2(min(4096.0 / amax, math.sqrt(2.0 ** 28 / max_sqn))))
+        bound = 0.5 * scale * scale * max_sqn * 1.01 + 1.0
+        pad_m = 4.0 * bound
+        shift = max(0, math.ceil(math.log2(pad_m / 32768.0)))
+        return scale, int(shift), float(pad_m)
+
     def _silhouette_tc(self, ctx, labels_list, ks, counts_list):
         K, comm = self.K, self.comm
         with self.span('sil_cells'):
@@ -421,15 +436,14 @@ class GroupingEngine:
             h = len(ks) // 2                                                   # too many cells: sweep twice
             return (self._silhouette_tc(ctx, labels_list[:h], ks[:h], counts_list[:h]) +
                     self._silhouette_tc(ctx, labels_list[h:], ks[h:], counts_list[h:]))
-        amax = float(K.absmax(ctx.Xc).item())
-        scale = 1.0 if amax <= 0 else 2.0 ** math.floor(math.log2(4096.0 / amax))
         with self.span('sil_pack'):
-            Xh, sqn = K.sil_pack(ctx.Xc, perm, P, scale)
+            scale, shift, pad_m = self.sil_scale(ctx.Xc)
+            Xh, aug = K.sil_pack(ctx.Xc, perm, P, scale, shift, pad_m)
             cellsum = K.zeros((G, P), torch.float32)
-        bounds = self._bounds(P // 128, 1)
+        bounds = self._bounds(P // 128, 2)       # even row-block ranges: CTA pairs share one 256-row MMA
         rb0, rb1 = bounds[comm.rank], bounds[comm.rank + 1]
         with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * ctx.d):
-            K.sil_sweep(Xh, sqn, scale, chunk_cell, G, rb0, rb1, cellsum)
+            K.sil_sweep(Xh, aug, scale, chunk_cell, G, rb0, rb1, cellsum)
         out = K.zeros((len(ks),), torch.float64)
         with self.span('sil_finish'):
             for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):

@@ -153,16 +153,18 @@ class CudaKernels:
         nv.call('vtf_absmax', ptr(X), c_i64(N), c_int(d), ptr(out), stream())
         return out
 
-    def sil_pack(self, X, perm, P, scale):
+    def sil_pack(self, X, perm, P, scale, shift, pad_m):
+        """fp16 operand [P,d] + augmented norm columns [2,P,16] (A and B flavour) for the tensor-core sweep."""
         N, d = self._chk(X)
         Xh = self.empty((P, d), torch.float16)
-        sqn = self.empty((P,), torch.float32)
-        nv.call('vtf_sil_pack', ptr(X), c_i64(N), c_int(d), ptr(perm), c_i64(P), c_f32(scale), ptr(Xh), ptr(sqn), stream())
-        return Xh, sqn
+        aug = self.empty((2, P, 16), torch.float16)
+        nv.call('vtf_sil_pack', ptr(X), c_i64(N), c_int(d), ptr(perm), c_i64(P), c_f32(scale), c_int(shift), c_f32(pad_m),
+                ptr(Xh), ptr(aug), None, stream())
+        return Xh, aug
 
-    def sil_sweep(self, Xh, sqn, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
+    def sil_sweep(self, Xh, aug, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
         P, d = Xh.shape
-        nv.call('vtf_sil_sweep', ptr(Xh), ptr(sqn), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
+        nv.call('vtf_sil_sweep', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
                 c_i64(rb_begin), c_i64(rb_end), ptr(cellsum), stream())
 
     def sil_finish_cells(self, cellsum, cell_to_cluster, k, perm, labels, counts, p_begin, p_end, out_slot):
