@@ -114,6 +114,11 @@ int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int 
 int vtf_dedup_init(uint64_t* key, int64_t N, void* stream);
 int vtf_cosine_dedup(const float* Xn, int64_t N, int d, int rank, int world,
                      uint64_t* key, void* stream);
+/* 'hash' branch (dupes.py:55-58; detection.py:57-59): bits[N,64] int64 0/1 average hashes (dupes.py:11-15)
+ * -> packed[N] uint64; key[i] = (min_{j<i} popc(h_i ^ h_j) << 32) | argmin_j, row 0 = 10000 << 32 (the
+ * reference's uint16 distance + 10000 mask).  Rows are owned in 256-row tiles, tile t by rank t % world.  */
+int vtf_hash_pack(const int64_t* bits, int64_t N, uint64_t* packed, void* stream);
+int vtf_hash_dedup(const uint64_t* packed, int64_t N, int rank, int world, uint64_t* key, void* stream);
 /* X_out[r,:] = X[idx[r],:]  -- np.delete(X, idx, axis=0) with idx = kept rows (dupes.py:68) */
 int vtf_gather_rows(const float* X, int d, const int64_t* idx, int64_t n_out, float* X_out,
                     void* stream);

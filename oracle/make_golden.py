@@ -24,6 +24,8 @@ import numpy as np
 ROOT = osp.dirname(osp.dirname(osp.abspath(__file__)))
 sys.path.insert(0, osp.join(ROOT, 'video-to-faces_b200'))
 from videotofaces_b200.synth import blobs, plant_dupes  # noqa: E402
+sys.path.insert(0, ROOT)
+from oracle.make_hashes import make_hashes  # noqa: E402
 
 for m in ('IPython', 'IPython.display'):
     mod = types.ModuleType(m)
@@ -73,6 +75,26 @@ def golden_dedup(name, X, thr):
     with open(osp.join(GOLD, name + '.log_dupes3.csv'), 'w') as f:
         f.write(log)
     return dict(stdout=out, n_kept=int(Xk.shape[0]))
+
+
+def golden_hash(name, H, thr):
+    with tempfile.TemporaryDirectory() as td:
+        paths = fake_faces(td, H.shape[0])
+        names = [osp.basename(p) for p in paths]          # detection.py hands over bare file names
+        os.makedirs(osp.join(td, 'intermediate'), exist_ok=True)
+        (Hk, goods), out = quiet(ref_dupes.remove_dupes_overall, H, names, ('hash', thr, True, td))
+        with open(osp.join(td, 'intermediate', 'log_dupes2.csv')) as f:
+            log = f.read()
+        kept = np.asarray([int(g[1:7]) for g in goods], dtype=np.int64)
+        rows = [l.split(',') for l in log.strip().split('\n')[1:]]
+        mins = np.asarray([int(r[2]) for r in rows], dtype=np.int64)
+        inds = np.asarray([int(r[1][1:7]) for r in rows], dtype=np.int64)
+        flag = np.asarray([int(r[3]) for r in rows], dtype=np.int8)
+    np.savez_compressed(osp.join(GOLD, name + '.npz'), kept=kept, mins=mins, inds=inds, flag=flag,
+                        n_out=np.int64(Hk.shape[0]), thr=np.int64(thr))
+    with open(osp.join(GOLD, name + '.log_dupes2.csv'), 'w') as f:
+        f.write(log)
+    return dict(stdout=out, n_kept=int(Hk.shape[0]))
 
 
 def golden_classify(name, X, R, thr):
@@ -126,6 +148,8 @@ def main():
     X = plant_dupes(blobs(300, 768, kc=3, noise=1.0, seed=3, normalize=False), frac=10, seed=2, normalize=False)[0]
     man['cases']['dedup_300x768'] = dict(gen="plant_dupes(blobs(300,768,kc=3,noise=1,seed=3,normalize=False),frac=10,seed=2,normalize=False)[0]",
                                          **golden_dedup('dedup_300x768', X, 0.25))
+
+    man['cases']['hash_500'] = dict(gen='oracle.make_hashes.make_hashes(500, seed=7); hash_thr=8', **golden_hash('hash_500', make_hashes(500, 7), 8))
 
     B = blobs(332, 512, kc=8, noise=1.0, seed=0)
     X, R = np.ascontiguousarray(B[:300]), np.ascontiguousarray(B[300:])

@@ -38,6 +38,18 @@ def dedup_core(X, threshold):
     return mins, inds, idx
 
 
+def hash_dedup_core(H, threshold):
+    """remove_dupes_overall, 'hash' branch (dupes.py:55-58, 62-65): H is [N,64] of 0/1 average hashes."""
+    import sklearn.metrics
+    D = sklearn.metrics.pairwise_distances(H, metric=lambda a, b: np.count_nonzero(a != b))   # dupes.py:56
+    D = D.astype(np.uint16)                                                                   # dupes.py:58
+    D += (1 - np.tri(H.shape[0], k=-1).astype(D.dtype)) * 10000
+    mins = D.min(axis=1)
+    inds = D.argmin(axis=1)
+    idx = (mins <= threshold).nonzero()[0]
+    return mins, inds, idx
+
+
 def dedup_apply(X, filenames, idx):
     """dupes.py:66-68: surviving rows and names, order preserved."""
     keep = np.ones(X.shape[0], dtype=bool)

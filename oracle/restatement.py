@@ -65,6 +65,19 @@ def dedup_core(X, threshold):
     return mins, inds, idx
 
 
+def hash_dedup_core(H, threshold):
+    """dupes.py:55-65, 'hash' branch: Hamming distance between 64-bit hashes, each row against earlier rows."""
+    Hb = np.asarray(H) != 0
+    N = Hb.shape[0]
+    mins = np.full(N, 10000, dtype=np.uint16)
+    inds = np.zeros(N, dtype=np.int64)
+    for i in range(1, N):
+        dd = (Hb[:i] != Hb[i]).sum(axis=1)
+        j = int(dd.argmin())
+        mins[i], inds[i] = dd[j], j
+    return mins, inds, (mins <= threshold).nonzero()[0]
+
+
 def classify_core(X, R, n_classes, thr):
     """grouping.py:51-56."""
     dist = cosine_distances(X, R)

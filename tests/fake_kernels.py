@@ -108,6 +108,18 @@ class FakeKernels:
             key[i] = (np.int64(D[i, j].view(np.uint32)) << 32) | j
         return torch.from_numpy(key)
 
+    def hash_dedup(self, bits, rank, world):
+        b = _np(bits) != 0
+        N = b.shape[0]
+        key = np.full(N, np.int64(10000) << 32, dtype=np.int64)
+        for i in range(1, N):
+            if (i // 256) % world != rank:
+                continue
+            dd = (b[:i] != b[i]).sum(1)
+            j = int(dd.argmin())
+            key[i] = (np.int64(dd[j]) << 32) | j
+        return torch.from_numpy(key)
+
     def _dist_matrix(self, X, sqn, rows):
         x = _np(X)
         g = x[rows] @ x.T

@@ -65,6 +65,27 @@ def test_remove_dupes_overall_golden(tmp_path, golden_dir, capsys, name, gen, th
     assert same_partner >= 0.99 * (len(want) - 1)
 
 
+def test_remove_dupes_overall_hash_golden(tmp_path, golden_dir, capsys):
+    """'hash' branch (detection.py:57-59 -> dupes.py:55-58): bit-exact against the real reference, log included."""
+    from oracle.make_hashes import make_hashes
+    g = gold(golden_dir, 'hash_500')
+    H = make_hashes(500, 7)
+    names = [osp.basename(p) for p in fake_faces(str(tmp_path), 500)]
+    os.makedirs(tmp_path / 'intermediate', exist_ok=True)
+    Hk, goods = vdupes.remove_dupes_overall(H, names, ('hash', 8, True, str(tmp_path)))
+    kept = np.asarray([int(n[1:7]) for n in goods])
+    assert np.array_equal(kept, g['kept']) and np.array_equal(Hk, H[g['kept']])
+    assert open(tmp_path / 'intermediate' / 'log_dupes2.csv').read() == read(golden_dir, 'hash_500.log_dupes2.csv')
+    assert sorted(os.listdir(tmp_path / 'intermediate' / 'dupes2')) == sorted(
+        'f%06d.jpg' % i for i in range(500) if i not in set(kept.tolist()))
+    assert 'Removed' not in capsys.readouterr().out                     # dupes.py:90 prints for 'enc' only
+    # a size the Python-callable reference would need hours for: compare with the numpy restatement on a slice
+    Hb = make_hashes(20000, 11)
+    mins, inds, idx = vdupes.get_engine().dedup_hash(Hb, 8)
+    rm, ri, _ = RS.hash_dedup_core(Hb[:3000], 8)
+    assert np.array_equal(mins[:3000], rm) and np.array_equal(inds[:3000], ri)
+
+
 @pytest.mark.parametrize('name,thr', [('classify_300x512_r32', 0.55), ('classify_300x512_r32_nothr', -1)])
 def test_classify_golden(tmp_path, golden_dir, name, thr):
     g = gold(golden_dir, name)

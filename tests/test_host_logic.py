@@ -101,6 +101,14 @@ def test_dedup_and_classify_decode(eng):
         assert np.array_equal(lab, rlab)
 
 
+def test_hash_dedup_decode(eng):
+    from oracle.make_hashes import make_hashes
+    H = make_hashes(300, 3)
+    mins, inds, idx = eng.dedup_hash(H, 8)
+    rmins, rinds, ridx = RC.hash_dedup_core(H, 8)
+    assert mins.dtype == np.uint16 and np.array_equal(mins, rmins) and np.array_equal(inds, rinds) and np.array_equal(idx, ridx)
+
+
 def test_four_rows_fail_like_the_reference(eng):
     X = blobs(4, 512, kc=2, noise=0.5, seed=0)
     ctx, res = eng.kmeans_sweep(X, [2, 3, 4], 0)

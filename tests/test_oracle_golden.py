@@ -47,6 +47,20 @@ def test_dedup_matches_reference(golden_dir, name, impl):
 
 
 @pytest.mark.parametrize('impl', [RC, RS])
+def test_hash_dedup_matches_reference(golden_dir, impl):
+    """'hash' branch (dupes.py:55-58): integer distances, so everything is bit-exact."""
+    from oracle.make_hashes import make_hashes
+    g = _gold(golden_dir, 'hash_500')
+    H = make_hashes(500, 7)
+    mins, inds, idx = impl.hash_dedup_core(H, int(g['thr']))
+    flag = np.zeros(500, dtype=np.int8)
+    flag[idx] = 1
+    assert np.array_equal(flag[1:], g['flag']) and np.array_equal(np.nonzero(flag == 0)[0], g['kept'])
+    assert np.array_equal(mins[1:].astype(np.int64), g['mins']) and np.array_equal(inds[1:], g['inds'])
+    assert mins[0] == 10000 and inds[0] == 0
+
+
+@pytest.mark.parametrize('impl', [RC, RS])
 @pytest.mark.parametrize('name,thr', [('classify_300x512_r32', 0.55), ('classify_300x512_r32_nothr', -1)])
 def test_classify_matches_reference(golden_dir, impl, name, thr):
     g = _gold(golden_dir, name)

@@ -33,6 +33,9 @@ def main():
     ap.add_argument('--rows', type=int, default=1_000_000)
     ap.add_argument('--dim', type=int, default=512)
     ap.add_argument('--k', type=int, default=6)
+    ap.add_argument('--only', default='', help='comma list of substrings: run only matching kernels (for ncu)')
+    ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--warm', type=int, default=2)
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -57,7 +60,12 @@ def main():
     R = X[:32].contiguous()
     rows = []
 
-    def add(name, ms, nbytes=None, flops=None):
+    only = [o for o in args.only.split(',') if o]
+
+    def add(name, fn, nbytes=None, flops=None, reps=None, warm=None):
+        if only and not any(o in name for o in only):
+            return
+        ms = timeit(fn, reps=reps or args.reps, warm=args.warm if warm is None else warm)
         r = dict(kernel=name, ms=ms)
         if nbytes:
             r.update(gbs=nbytes / ms / 1e6, hbm_frac=nbytes / ms / 1e6 / pk['hbm_gbs'], bytes=nbytes)
@@ -66,23 +74,23 @@ def main():
         rows.append(r)
 
     B = N * d * 4
-    add('normalize_rows', timeit(lambda: K.normalize_rows(X)), 2 * B)
-    add('row_sqnorms', timeit(lambda: K.row_sqnorms(X)), B)
-    add('col_stats', timeit(lambda: K.col_stats(X)), B)
-    add('center_rows', timeit(lambda: K.center_rows(X, mean)), 2 * B)
-    add('kpp_dist T=3', timeit(lambda: K.kpp_dist(X, X[:3].contiguous(), closest)), B + 3 * N * 4 + N * 4)
-    add('kpp_pick (sequential fp32 chain)', timeit(lambda: K.kpp_pick(closest, thr)), N * 4)
-    add('lloyd_assign k=%d' % k, timeit(lambda: K.lloyd_assign(X, C, labels, counts, nch)), B + N * 8, 2.0 * N * k * d)
-    add('cluster_sums k=%d' % k, timeit(lambda: K.cluster_sums(X, labels, k)), B + N * 4)
-    add('cluster_dispersion k=%d' % k, timeit(lambda: K.cluster_dispersion(X, labels, C64)), B + N * 4)
-    add('cosine_classify R=32', timeit(lambda: K.cosine_classify(X, R, 0.9)), B + N * 32 * 4 + N * 8, 2.0 * N * 32 * d)
+    add('normalize_rows', lambda: K.normalize_rows(X), 2 * B)
+    add('row_sqnorms', lambda: K.row_sqnorms(X), B)
+    add('col_stats', lambda: K.col_stats(X), B)
+    add('center_rows', lambda: K.center_rows(X, mean), 2 * B)
+    add('kpp_dist T=3', lambda: K.kpp_dist(X, X[:3].contiguous(), closest), B + 3 * N * 4 + N * 4)
+    add('kpp_pick (sequential fp32 chain)', lambda: K.kpp_pick(closest, thr), N * 4)
+    add('lloyd_assign k=%d' % k, lambda: K.lloyd_assign(X, C, labels, counts, nch), B + N * 8, 2.0 * N * k * d)
+    add('cluster_sums k=%d' % k, lambda: K.cluster_sums(X, labels, k), B + N * 4)
+    add('cluster_dispersion k=%d' % k, lambda: K.cluster_dispersion(X, labels, C64), B + N * 4)
+    add('cosine_classify R=32', lambda: K.cosine_classify(X, R, 0.9), B + N * 32 * 4 + N * 8, 2.0 * N * 32 * d)
     nd = min(N, 50_000)
     Xd = X[:nd].contiguous()
-    add('cosine_dedup N=%d (fp32 FMA)' % nd, timeit(lambda: K.cosine_dedup(Xd, 0, 1), reps=3, warm=1), None, float(nd) * nd * d)
+    add('cosine_dedup N=%d (fp32 FMA)' % nd, lambda: K.cosine_dedup(Xd, 0, 1), None, float(nd) * nd * d)
     perm = torch.arange(N, device='cuda')
     P = ((N + 255) // 256) * 256
     perm = torch.cat([perm, torch.full((P - N,), -1, device='cuda', dtype=torch.int64)])
-    add('sil_pack', timeit(lambda: K.sil_pack(X, perm, P, 1024.0, 6, 4.0 * 0.5 * 1024.0 ** 2 * 1.02)), B + N * d * 2)
+    add('sil_pack', lambda: K.sil_pack(X, perm, P, 1024.0, 6, 4.0 * 0.5 * 1024.0 ** 2 * 1.02), B + N * d * 2)
     json.dump(dict(rows=args.rows, dim=d, peaks=dict(hbm_gbs=pk['hbm_gbs'], bf16_tflops_sustained=pk.get('bf16_tflops_sustained')),
                    kernels=rows), sys.stdout, indent=1)
     print()

@@ -169,3 +169,81 @@ int vtf_silhouette_rowsums_exact(const float* X, const float* sqnorm, int64_t N,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// 'hash' branch of remove_dupes_overall (dupes.py:55-58, called from detection.py:57-59): all-pairs
+// Hamming distance between 64-bit average hashes (dupes.py:11-15), each row against every EARLIER row.
+// The reference evaluates a Python callable N^2 times (SK/metrics/pairwise.py:2034-2051); here one
+// thread owns a row, hashes stream through shared memory, distance = popc(xor).
+namespace vtf {
+
+// warp per row: bits[N,64] int64 (0/1, the layout ahash() returns after np.stack) -> one uint64 per row
+__global__ void __launch_bounds__(256) hash_pack_kernel(const long long* __restrict__ bits, int64_t N,
+                                                        unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (; row < N; row += stride) {
+        const unsigned lo = __ballot_sync(0xffffffffu, bits[row * 64 + lane] != 0);
+        const unsigned hi = __ballot_sync(0xffffffffu, bits[row * 64 + 32 + lane] != 0);
+        if (lane == 0) out[row] = ((unsigned long long)hi << 32) | lo;
+    }
+}
+
+constexpr int kHashRows = 256, kHashCols = 1024;
+
+__global__ void __launch_bounds__(kHashRows) hash_dedup_kernel(const unsigned long long* __restrict__ h, int64_t N,
+                                                               int64_t tile0, int64_t tile_stride,
+                                                               unsigned long long* __restrict__ key) {
+    __shared__ unsigned long long sh[kHashCols];
+    const int64_t ti = tile0 + (int64_t)blockIdx.x * tile_stride;
+    const int64_t i = ti * kHashRows + threadIdx.x;
+    const unsigned long long hi = i < N ? h[i] : 0ull;
+    unsigned long long best = ~0ull;
+    const int64_t jend = min(N, (ti + 1) * kHashRows);        // columns j < i only
+    for (int64_t j0 = 0; j0 < jend; j0 += kHashCols) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kHashCols; t += kHashRows) sh[t] = (j0 + t < N) ? h[j0 + t] : 0ull;
+        __syncthreads();
+        const int lim = (int)min((int64_t)kHashCols, i - j0);   // j < i
+        for (int t = 0; t < lim; ++t) {
+            const unsigned long long k = ((unsigned long long)__popcll(hi ^ sh[t]) << 32) | (unsigned long long)(j0 + t);
+            best = k < best ? k : best;                         // ascending j: first index wins ties
+        }
+    }
+    if (i < N && i > 0) key[i] = best;
+}
+
+__global__ void hash_init_kernel(unsigned long long* key, int64_t N) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) key[i] = 10000ull << 32;                         // dupes.py:62 in uint16 arithmetic
+}
+
+}  // namespace vtf
+
+extern "C" {
+
+int vtf_hash_pack(const int64_t* bits, int64_t N, uint64_t* packed, void* stream) {
+    VTF_REQUIRE(bits && packed && N >= 0, "vtf_hash_pack");
+    if (N == 0) return VTF_OK;
+    const int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    VTF_LAUNCH(hash_pack_kernel, grid, 256, 0, stream, (const long long*)bits, N, (unsigned long long*)packed);
+    VTF_CHECK_LAST("vtf_hash_pack");
+    return VTF_OK;
+}
+
+int vtf_hash_dedup(const uint64_t* packed, int64_t N, int rank, int world, uint64_t* key, void* stream) {
+    VTF_REQUIRE(packed && key && N >= 0 && world > 0 && rank >= 0 && rank < world, "vtf_hash_dedup");
+    if (N == 0) return VTF_OK;
+    VTF_LAUNCH(hash_init_kernel, (unsigned)((N + 255) / 256), 256, 0, stream, (unsigned long long*)key, N);
+    VTF_CHECK_LAST("vtf_hash_dedup/init");
+    const int64_t nt = (N + kHashRows - 1) / kHashRows;
+    if (rank >= nt) return VTF_OK;
+    const int64_t mine = (nt - rank + world - 1) / world;
+    VTF_LAUNCH(hash_dedup_kernel, (unsigned)mine, kHashRows, 0, stream, (const unsigned long long*)packed, N,
+               (int64_t)rank, (int64_t)world, (unsigned long long*)key);
+    VTF_CHECK_LAST("vtf_hash_dedup");
+    return VTF_OK;
+}
+
+}  // extern "C"

@@ -121,21 +121,28 @@ __global__ void __launch_bounds__(128) kpp_pick_kernel(const float* __restrict__
             const int64_t base = c * kPickChunk;
             // software pipeline: the 4 x LDS.128 of block i+1 are in flight while the 16-add chain of
             // block i (the critical path: 16 x 4 cycles) runs
-            float4 n0 = b4[0], n1 = b4[1], n2 = b4[2], n3 = b4[3];
+            float4 nq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nq[u] = b4[u];
 #pragma unroll 1
-            for (int i = 0; i < kPickChunk / 4; i += 4) {
-                const float4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-                if (i + 4 < kPickChunk / 4) { n0 = b4[i + 4]; n1 = b4[i + 5]; n2 = b4[i + 6]; n3 = b4[i + 7]; }
+            for (int i = 0; i < kPickChunk / 4; i += 8) {      // 32 elements per block: one compare per 32 adds
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q[u] = nq[u];
+                if (i + 8 < kPickChunk / 4) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) nq[u] = b4[i + 8 + u];
+                }
                 float e = s;
-                e = __fadd_rn(e, q0.x); e = __fadd_rn(e, q0.y); e = __fadd_rn(e, q0.z); e = __fadd_rn(e, q0.w);
-                e = __fadd_rn(e, q1.x); e = __fadd_rn(e, q1.y); e = __fadd_rn(e, q1.z); e = __fadd_rn(e, q1.w);
-                e = __fadd_rn(e, q2.x); e = __fadd_rn(e, q2.y); e = __fadd_rn(e, q2.z); e = __fadd_rn(e, q2.w);
-                e = __fadd_rn(e, q3.x); e = __fadd_rn(e, q3.y); e = __fadd_rn(e, q3.z); e = __fadd_rn(e, q3.w);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    e = __fadd_rn(e, q[u].x); e = __fadd_rn(e, q[u].y); e = __fadd_rn(e, q[u].z); e = __fadd_rn(e, q[u].w);
+                }
                 if (e >= th) {
                     float r = s;
                     const float* bs = buf[c & 1] + 4 * i;   // rare: replay the block element by element
 #pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 32; ++j) {
                         r = __fadd_rn(r, bs[j]);
                         while (r >= th) {      // searchsorted side='left': first i with cumsum[i] >= v
                             const int64_t g = base + 4 * i + j;

@@ -21,8 +21,9 @@ int num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------
-// warp per row: |x|^2 in fp32 (lanes own interleaved float4 columns), optional normalise.
-template <bool NORMALIZE>
+// warp per row: |x|^2 in fp32 (lanes own interleaved float4 columns), optional normalise.  The row stays
+// in registers between the norm and the divide (DV float4 per lane, d = 128*DV), so X is read exactly once.
+template <bool NORMALIZE, int DV>
 __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ X, int64_t N, int d,
                                                        float* __restrict__ Xn, float* __restrict__ sqn) {
     const int lane = threadIdx.x & 31;
@@ -31,10 +32,21 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (; row < N; row += stride) {
         const float4* xr = reinterpret_cast<const float4*>(X + row * d);
+        float4 xv[DV > 0 ? DV : 1];
         float s = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-            float4 a = ldg_stream(xr + v);
-            s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+        if (DV > 0) {
+#pragma unroll
+            for (int v = 0; v < DV; ++v) xv[v] = ldg_stream(xr + lane + 32 * v);
+#pragma unroll
+            for (int v = 0; v < DV; ++v) {
+                s = fmaf(xv[v].x, xv[v].x, s); s = fmaf(xv[v].y, xv[v].y, s);
+                s = fmaf(xv[v].z, xv[v].z, s); s = fmaf(xv[v].w, xv[v].w, s);
+            }
+        } else {
+            for (int v = lane; v < nvec; v += 32) {
+                float4 a = __ldg(xr + v);
+                s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+            }
         }
         s = warp_sum(s);
         if (sqn && lane == 0) sqn[row] = s;
@@ -43,14 +55,38 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
             // SK/preprocessing/_data.py:127-132: norms below 10*eps are replaced by 1
             if (nrm < 10.f * 1.1920929e-07f) nrm = 1.f;
             float4* outr = reinterpret_cast<float4*>(Xn + row * d);
-            for (int v = lane; v < nvec; v += 32) {
-                float4 a = __ldg(xr + v);   // second touch comes from L1/L2
-                a.x = __fdiv_rn(a.x, nrm); a.y = __fdiv_rn(a.y, nrm);
-                a.z = __fdiv_rn(a.z, nrm); a.w = __fdiv_rn(a.w, nrm);
-                outr[v] = a;
+            if (DV > 0) {
+#pragma unroll
+                for (int v = 0; v < DV; ++v) {
+                    float4 a = xv[v];
+                    a.x = __fdiv_rn(a.x, nrm); a.y = __fdiv_rn(a.y, nrm);
+                    a.z = __fdiv_rn(a.z, nrm); a.w = __fdiv_rn(a.w, nrm);
+                    outr[lane + 32 * v] = a;
+                }
+            } else {
+                for (int v = lane; v < nvec; v += 32) {
+                    float4 a = __ldg(xr + v);   // second touch comes from L1/L2
+                    a.x = __fdiv_rn(a.x, nrm); a.y = __fdiv_rn(a.y, nrm);
+                    a.z = __fdiv_rn(a.z, nrm); a.w = __fdiv_rn(a.w, nrm);
+                    outr[v] = a;
+                }
             }
         }
     }
+}
+
+template <bool NORMALIZE>
+static int launch_row_norm(const float* X, int64_t N, int d, float* Xn, float* sqn, void* stream, const char* what) {
+    const int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    const int dv = (d % 128 == 0 && d / 128 <= 8) ? d / 128 : 0;
+#define VTF_RN_CASE(DVv) case DVv: VTF_LAUNCH((row_norm_kernel<NORMALIZE, DVv>), grid, 256, 0, stream, X, N, d, Xn, sqn); break;
+    switch (dv) {
+        VTF_RN_CASE(0) VTF_RN_CASE(1) VTF_RN_CASE(2) VTF_RN_CASE(3) VTF_RN_CASE(4)
+        VTF_RN_CASE(5) VTF_RN_CASE(6) VTF_RN_CASE(7) VTF_RN_CASE(8)
+    }
+#undef VTF_RN_CASE
+    VTF_CHECK_LAST(what);
+    return VTF_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -142,19 +178,13 @@ int vtf_device_check(void) {
 int vtf_normalize_rows(const float* X, int64_t N, int d, float* Xn, void* stream) {
     VTF_REQUIRE(X && Xn && N >= 0 && d > 0 && d % 4 == 0, "vtf_normalize_rows");
     if (N == 0) return VTF_OK;
-    int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
-    VTF_LAUNCH(row_norm_kernel<true>, grid, 256, 0, stream, X, N, d, Xn, (float*)nullptr);
-    VTF_CHECK_LAST("vtf_normalize_rows");
-    return VTF_OK;
+    return launch_row_norm<true>(X, N, d, Xn, (float*)nullptr, stream, "vtf_normalize_rows");
 }
 
 int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* stream) {
     VTF_REQUIRE(X && sqnorm && N >= 0 && d > 0 && d % 4 == 0, "vtf_row_sqnorms");
     if (N == 0) return VTF_OK;
-    int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
-    VTF_LAUNCH(row_norm_kernel<false>, grid, 256, 0, stream, X, N, d, (float*)nullptr, sqnorm);
-    VTF_CHECK_LAST("vtf_row_sqnorms");
-    return VTF_OK;
+    return launch_row_norm<false>(X, N, d, (float*)nullptr, sqnorm, stream, "vtf_row_sqnorms");
 }
 
 size_t vtf_col_stats_ws_bytes(int d) { return (size_t)col_stats_grid() * 2 * (size_t)d * sizeof(double); }

@@ -64,27 +64,50 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
 
     unsigned int my_changed = 0;
     const int64_t warps_total = (int64_t)gridDim.x * nwarps;
-    for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * kRowsPerWarp; row0 < N;
-         row0 += warps_total * kRowsPerWarp) {
+    const int64_t step = warps_total * kRowsPerWarp;
+    int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * kRowsPerWarp;
+
+    // Software pipeline: the rows (and, for Lloyd, the previous labels) of iteration i+1 are requested before
+    // the dot products of iteration i start, so every warp keeps 4 KB of HBM reads in flight while it computes.
+    float4 n0[DV > 0 ? DV : 1], n1[DV > 0 ? DV : 1];
+    int old0 = -1, old1 = -1;
+    auto prefetch = [&](int64_t r0) {
+        if (r0 >= N) return;
+        const float4* a0 = reinterpret_cast<const float4*>(X + r0 * d);
+        const float4* a1 = reinterpret_cast<const float4*>(X + (r0 + 1 < N ? r0 + 1 : r0) * d);
+        if (DV > 0) {
+#pragma unroll
+            for (int v = 0; v < DV; ++v) { n0[v] = ldg_stream(a0 + lane + 32 * v); n1[v] = ldg_stream(a1 + lane + 32 * v); }
+        }
+        if (MODE == 0 && lane == 0) {
+            old0 = le.labels[r0];
+            old1 = (r0 + 1 < N) ? le.labels[r0 + 1] : -1;
+        }
+    };
+    prefetch(row0);
+    for (; row0 < N; row0 += step) {
         const bool has1 = (row0 + 1 < N);
         const float4* x0p = reinterpret_cast<const float4*>(X + row0 * d);
         const float4* x1p = reinterpret_cast<const float4*>(X + (has1 ? row0 + 1 : row0) * d);
         float4 x0[DV > 0 ? DV : 1], x1[DV > 0 ? DV : 1];
         if (DV > 0) {
 #pragma unroll
-            for (int v = 0; v < DV; ++v) { x0[v] = ldg_stream(x0p + lane + 32 * v); x1[v] = ldg_stream(x1p + lane + 32 * v); }
+            for (int v = 0; v < DV; ++v) { x0[v] = n0[v]; x1[v] = n1[v]; }
         }
+        const int prev0 = old0, prev1 = old1;
+        prefetch(row0 + step);
         float best0 = INFINITY, best1 = INFINITY;
         int arg0 = 0, arg1 = 0;
         float keep0 = 0.f, keep1 = 0.f;   // classify: lane (c & 31) keeps distance c for the coalesced store
         for (int c = 0; c < k; ++c) {
             const float4* cr = reinterpret_cast<const float4*>(C_SMEM ? sC + (size_t)c * d : C + (size_t)c * d);
-            float p0 = 0.f, p1 = 0.f;
+            float p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;   // two partial sums per row: shorter FMA chains
             if (DV > 0) {
 #pragma unroll
                 for (int v = 0; v < DV; ++v) {
                     float4 cv = C_SMEM ? cr[lane + 32 * v] : __ldg(cr + lane + 32 * v);
-                    p0 = dot4(x0[v], cv, p0); p1 = dot4(x1[v], cv, p1);
+                    if (v & 1) { q0 = dot4(x0[v], cv, q0); q1 = dot4(x1[v], cv, q1); }
+                    else { p0 = dot4(x0[v], cv, p0); p1 = dot4(x1[v], cv, p1); }
                 }
             } else {
                 for (int v = lane; v < nvec; v += 32) {
@@ -92,7 +115,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
                     p0 = dot4(__ldg(x0p + v), cv, p0); p1 = dot4(__ldg(x1p + v), cv, p1);
                 }
             }
-            p0 = warp_sum(p0); p1 = warp_sum(p1);
+            p0 = warp_sum(p0 + q0); p1 = warp_sum(p1 + q1);
             float s0, s1;
             if (MODE == 0) {
                 const float c2 = sC2[c];
@@ -113,11 +136,11 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
         }
         if (lane == 0) {
             if (MODE == 0) {
-                if (le.labels[row0] != arg0) ++my_changed;
+                if (prev0 != arg0) ++my_changed;
                 le.labels[row0] = arg0;
                 atomicAdd(&s_counts[arg0], 1u);
                 if (has1) {
-                    if (le.labels[row0 + 1] != arg1) ++my_changed;
+                    if (prev1 != arg1) ++my_changed;
                     le.labels[row0 + 1] = arg1;
                     atomicAdd(&s_counts[arg1], 1u);
                 }
@@ -145,7 +168,7 @@ static int launch_rowdot(const float* X, int64_t N, int d, const float* C, int k
     const bool c_smem = (c_bytes + small) <= 200 * 1024;
     const size_t smem = (c_smem ? c_bytes : 0) + small;
     const int dv = (d % 128 == 0 && d / 128 <= kMaxDV) ? d / 128 : 0;
-    int blocks_per_sm = c_smem ? (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / (smem + 1024))) : 4;
+    int blocks_per_sm = c_smem ? (int)max((size_t)1, min((size_t)3, (size_t)(220 * 1024) / (smem + 1024))) : 3;
     int64_t want = (N + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp);
     int grid = (int)max((int64_t)1, min((int64_t)num_sms() * blocks_per_sm, want));
 

@@ -32,6 +32,8 @@ SIGNATURES = {
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    'vtf_hash_pack': (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'vtf_hash_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     'vtf_gather_rows': (c_int, [c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
     'vtf_silhouette_rowsums_exact': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     'vtf_row_sqnorms': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),

@@ -1,10 +1,10 @@
 """Duplicate removal over embeddings -- drop-in for videotofaces.dupes.remove_dupes_overall
 (/root/reference/src/videotofaces/dupes.py:51-92).
 
-The 'enc' branch (cosine distance to every EARLIER row, mark when min <= thr) runs on the GPU and
-never materialises the N x N matrix; file moves and log_dupes3.csv keep the reference's format.
-The 'hash' branch belongs to the detection stage (dupes.py:55-58, called from detection.py:59) and
-is the first "next" row of SURVEY.md section 8f; it is not built yet and says so.
+Both branches run on the GPU and never materialise the N x N matrix: 'enc' (cosine distance to every
+EARLIER row, mark when min <= thr; called from main.py:74) and 'hash' (Hamming distance between 64-bit
+average hashes, dupes.py:55-58, called from detection.py:57-59 -- the first "next" row of SURVEY.md
+section 8f).  File moves and log_dupes{2,3}.csv keep the reference's format.
 """
 import os
 import os.path as osp
@@ -25,30 +25,35 @@ def _write_dupes_log(path, filenames, mins, inds, is_dup, measure_name):
 def remove_dupes_overall(X, filenames, dup_params):
     """Returns (X_kept float32 [N - n_dup, d], goods) exactly like dupes.py:51-92."""
     measure_type, threshold, save_dupes, out_dir = dup_params
-    if measure_type == 'hash':
-        raise NotImplementedError("remove_dupes_overall('hash') is part of the detection stage "
-                                  "(dupes.py:55-58) and is not built in videotofaces_b200 yet")
     eng = get_engine()
     n = X.shape[0]
-    mins, inds, idx = eng.dedup(X, threshold)                                  # dupes.py:60-65
+    is_hash = measure_type == 'hash'
+    if is_hash:
+        mins, inds, idx = eng.dedup_hash(X, threshold)                         # dupes.py:55-58, 62-65
+    else:
+        mins, inds, idx = eng.dedup(X, threshold)                              # dupes.py:60-65
     is_dup = np.zeros(n, dtype=bool)
     is_dup[idx] = True
     dupes = [fn for i, fn in enumerate(filenames) if is_dup[i]]                # dupes.py:66-67
     goods = [fn for i, fn in enumerate(filenames) if not is_dup[i]]
-    X_kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
+    if is_hash:
+        X_kept = np.delete(np.asarray(X), idx, axis=0)                         # 64 ints per row: host bookkeeping
+    else:
+        X_kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
 
     face_dir = osp.join(out_dir, 'faces')
     if not save_dupes:                                                         # dupes.py:70-74
         for fn in dupes:
             os.remove(osp.join(face_dir, osp.basename(fn)))
     else:                                                                      # dupes.py:75-88
-        dup_dir = osp.join(out_dir, 'intermediate', 'dupes3')
+        mdigit, mname = ('2', 'hash_diff') if is_hash else ('3', 'distance')
+        dup_dir = osp.join(out_dir, 'intermediate', 'dupes' + mdigit)
         os.makedirs(dup_dir, exist_ok=True)
         for fn in dupes:
             base = osp.basename(fn)
             os.replace(osp.join(face_dir, base), osp.join(dup_dir, base))
-        _write_dupes_log(osp.join(out_dir, 'intermediate', 'log_dupes3.csv'), filenames, mins, inds, is_dup, 'distance')
+        _write_dupes_log(osp.join(out_dir, 'intermediate', 'log_dupes' + mdigit + '.csv'), filenames, mins, inds, is_dup, mname)
 
-    if idx.any():                                                              # dupes.py:90-91
+    if not is_hash and idx.any():                                              # dupes.py:90-91
         print('Removed %u near-duplicates' % idx.shape[0])
     return X_kept, goods

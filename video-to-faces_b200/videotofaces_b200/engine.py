@@ -106,6 +106,22 @@ class GroupingEngine:
         idx = (mins <= np.float32(threshold)).nonzero()[0]                    # dupes.py:65, fp32 compare
         return mins, inds, idx
 
+    def dedup_hash(self, H, threshold):
+        """dupes.py:55-65, 'hash' branch: H is [N,64] of 0/1 (np.stack of ahash vectors).  Returns
+        (mins uint16 [N], inds int64 [N], idx int64 [n_dup]) -- D is cast to uint16 by the reference (:58)."""
+        H = np.ascontiguousarray(np.asarray(H) != 0, dtype=np.int64)
+        if H.ndim != 2 or H.shape[1] != 64:
+            raise ValueError('hash dedup expects [N,64] average hashes (dupes.py:11-15)')
+        if H.shape[0] == 0:
+            return np.zeros(0, np.uint16), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        key = self.K.hash_dedup(torch.from_numpy(H).to(self.device), self.comm.rank, self.comm.world)
+        self.comm.allreduce_min(key)
+        key_h = key.cpu().numpy()
+        mins = (key_h >> 32).astype(np.uint16)
+        inds = (key_h & 0xffffffff).astype(np.int64)
+        idx = (mins <= threshold).nonzero()[0]
+        return mins, inds, idx
+
     def delete_rows(self, X, idx):
         """np.delete(X, idx, axis=0) (dupes.py:68) on the device; returns a device tensor."""
         X = self.to_device(X)

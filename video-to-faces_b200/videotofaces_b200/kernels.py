@@ -136,6 +136,15 @@ class CudaKernels:
         nv.call('vtf_cosine_dedup', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
         return key
 
+    def hash_dedup(self, bits, rank, world):
+        """bits: int64 [N,64] of 0/1 -> packed (distance, argmin) keys, int64 [N]."""
+        N = bits.shape[0]
+        packed = self.empty((N,), torch.int64)
+        key = self.empty((N,), torch.int64)
+        nv.call('vtf_hash_pack', ptr(bits), c_i64(N), ptr(packed), stream())
+        nv.call('vtf_hash_dedup', ptr(packed), c_i64(N), c_int(rank), c_int(world), ptr(key), stream())
+        return key
+
     # ------------------------------------------------------------------ a8
     def sil_rowsums_exact(self, X, sqn, labels, k, row_begin, row_end, rowsum):
         N, d = self._chk(X)
