@@ -114,6 +114,17 @@ int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int 
 int vtf_dedup_init(uint64_t* key, int64_t N, void* stream);
 int vtf_cosine_dedup(const float* Xn, int64_t N, int d, int rank, int world,
                      uint64_t* key, void* stream);
+/* Tensor-core form of the same (tcgen05, CTA pairs; used for large N).  Decisions must match an fp32 SGEMM,
+ * so pack splits scale*Xn into two fp16 pieces hi + lo (22 significant bits; rows >= N zero, P % 256 == 0)
+ * and the sweep accumulates hi.hi + hi.lo + lo.hi in fp32 in TMEM, then applies the same
+ * clip(1 - S, 0, 2) / j < i / min / first-argmin epilogue.  Units of 256 rows, unit u owned by rank u % world
+ * (counted from the bottom so the triangular work balances).  key as for vtf_cosine_dedup.   */
+int vtf_dedup_pack(const float* Xn, int64_t N, int d, int64_t P, float scale, void* Hi, void* Lo, void* stream);
+int vtf_cosine_dedup_tc(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale,
+                        int rank, int world, uint64_t* key, void* stream);
+/* The tensor core accumulates fp32 with truncation (~3e-6 relative after 96 steps): refine re-evaluates
+ * every owned row's winner, key[i] = (bits(clip(1 - xn_i.xn_j, 0, 2)) << 32) | j with an exact fp32 dot.  */
+int vtf_dedup_refine(const float* Xn, int64_t N, int d, int rank, int world, uint64_t* key, void* stream);
 /* 'hash' branch (dupes.py:55-58; detection.py:57-59): bits[N,64] int64 0/1 average hashes (dupes.py:11-15)
  * -> packed[N] uint64; key[i] = (min_{j<i} popc(h_i ^ h_j) << 32) | argmin_j, row 0 = 10000 << 32 (the
  * reference's uint16 distance + 10000 mask).  Rows are owned in 256-row tiles, tile t by rank t % world.  */

@@ -135,6 +135,21 @@ def test_dedup_kernel(engine, N, d, thr):
     assert (inds == rinds).mean() > 0.99 and inds[0] == 0 and mins[0] == np.float32(10000.0)
 
 
+@pytest.mark.parametrize('N,d,thr', [(3000, 512, 0.2), (2500, 768, 0.25), (1000, 1024, 0.2), (300, 64, 0.2), (9000, 512, 0.2), (2, 512, 0.2)])
+def test_dedup_tensor_core_kernel(engine, N, d, thr):
+    """tcgen05 dedup (split fp16, three MMAs per K step) against the scikit-learn oracle: exact duplicate set
+    (ties within 1e-6 of the threshold reported), logged distances as accurate as an fp32 GEMM."""
+    X = plant_dupes(blobs(N, d, kc=4, seed=5, normalize=(d == 512)), frac=20, seed=1, normalize=(d == 512))[0]
+    mins, inds, idx = engine.dedup(X, thr, force='tc')
+    rmins, rinds, ridx = RC.dedup_core(X, thr)
+    ties = np.abs(rmins - np.float32(thr)) <= 1e-6
+    assert np.array_equal(np.setdiff1d(idx, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
+    np.testing.assert_allclose(mins, rmins, rtol=2e-6, atol=4e-7)          # fp32-GEMM accuracy, not fp16
+    assert (inds == rinds).mean() > 0.99 and inds[0] == 0 and mins[0] == np.float32(10000.0)
+    smins, sinds, sidx = engine.dedup(X, thr, force='simt')
+    assert np.array_equal(sidx, idx) or ties.any()
+
+
 @pytest.mark.parametrize('N,d,k', [(500, 512, 3), (1000, 768, 5), (130, 64, 2)])
 def test_silhouette_exact_kernel(engine, N, d, k):
     X = blobs(N, d, kc=k, seed=3, normalize=(d == 512))

@@ -45,7 +45,9 @@ def main():
             X, src, dst = plant_dupes(np.ascontiguousarray(B[:N]), frac=50, seed=1)
             R = np.ascontiguousarray(B[N:])
             Xd = eng.to_device(X)
+            eng.dedup(Xd[:8192].contiguous(), 0.2)   # warm
             (mins, inds, idx), t_dedup = timed(lambda: eng.dedup(Xd, 0.2))
+            (smins, _, sidx), t_simt = timed(lambda: eng.dedup(Xd, 0.2, force='simt'))
             (dist, lab), t_cls = timed(lambda: eng.classify(Xd, R, 0.55))
             sub = np.sort(np.random.default_rng(0).choice(N, 64, replace=False))
             D = RS.cosine_distances(X[sub], X)
@@ -54,7 +56,8 @@ def main():
             ok_cls = bool(np.array_equal(np.where(Dr.min(1) >= np.float32(0.55), 32, Dr.argmin(1)), lab[sub]))
             print(json.dumps(dict(config='c2', rows=N, dim=512, dedup_s=t_dedup, classify_s=t_cls, n_dupes=int(idx.size),
                                   emb_per_s=N / (t_dedup + t_cls), dedup_rows_match_oracle=bool(ok_rows),
-                                  classify_rows_match_oracle=ok_cls, dedup_tflops=N * N * 512.0 / t_dedup / 1e12)))
+                                  classify_rows_match_oracle=ok_cls, dedup_tflops=N * N * 512.0 / t_dedup / 1e12, dedup_simt_s=t_simt,
+                                  tc_equals_simt_set=bool(np.array_equal(idx, sidx)), max_abs_min_diff=float(np.abs(mins - smins).max()))))
         elif name in ('c4', 'c5', 'c3'):
             if name == 'c4':   # 1M x 1024, k = 2..32, clusters-save-all
                 N, d, ks, kc, norm = int(1_000_000 * args.scale), 1024, list(range(2, 33)), 16, False

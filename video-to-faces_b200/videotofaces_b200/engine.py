@@ -19,6 +19,7 @@ import torch
 from .dist import Comm, shard_bounds
 
 TC_MIN_ROWS = 4096        # below this the exact fp32 silhouette kernel is used (and is fast enough)
+TC_DEDUP_MIN_ROWS = 8192  # below this the fp32 FMA dedup kernel is used
 TC_MAX_CELLSUM_BYTES = 32 << 30
 
 
@@ -91,14 +92,21 @@ class GroupingEngine:
         return shard_bounds(n, self.comm.world, align)
 
     # ------------------------------------------------------------------------------ a1 dedup
-    def dedup(self, X, threshold):
-        """dupes.py:60-65.  Returns (mins fp32 [N], inds int64 [N], idx int64 [n_dup]) as numpy."""
+    def dedup(self, X, threshold, force=None):
+        """dupes.py:60-65.  Returns (mins fp32 [N], inds int64 [N], idx int64 [n_dup]) as numpy.
+        Large inputs run on the tensor cores (split-fp16, fp32-GEMM accuracy), small ones on the fp32 pipe;
+        `force` = 'tc' | 'simt' overrides the choice."""
         X = self.to_device(X)
-        N = X.shape[0]
+        N, d = X.shape
         if N == 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64)
         Xn = self.K.normalize_rows(X)
-        key = self.K.cosine_dedup(Xn, self.comm.rank, self.comm.world)
+        tc_ok = d % 64 == 0 and 64 <= d <= 4096 and hasattr(self.K, 'cosine_dedup_tc')
+        use_tc = (tc_ok and N >= TC_DEDUP_MIN_ROWS) if force is None else (force == 'tc')
+        if use_tc and not tc_ok:
+            raise ValueError('tensor-core dedup needs d % 64 == 0')
+        with self.span('dedup', flops=float(N) * N * d):
+            key = (self.K.cosine_dedup_tc if use_tc else self.K.cosine_dedup)(Xn, self.comm.rank, self.comm.world)
         self.comm.allreduce_min(key)
         key_h = key.cpu().numpy()
         mins = (key_h >> 32).astype(np.uint32).view(np.float32)

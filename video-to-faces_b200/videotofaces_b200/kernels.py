@@ -136,6 +136,21 @@ class CudaKernels:
         nv.call('vtf_cosine_dedup', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
         return key
 
+    def cosine_dedup_tc(self, Xn, rank, world):
+        """Tensor-core dedup: split-fp16 operands (hi + lo), three MMAs per K step, fp32 accumulate."""
+        N, d = self._chk(Xn)
+        P = ((N + 255) // 256) * 256
+        scale = 4096.0                      # |xn| <= 1: hi keeps 11 bits, lo the next 11
+        hi = self.empty((P, d), torch.float16)
+        lo = self.empty((P, d), torch.float16)
+        key = self.empty((N,), torch.int64)
+        nv.call('vtf_dedup_pack', ptr(Xn), c_i64(N), c_int(d), c_i64(P), c_f32(scale), ptr(hi), ptr(lo), stream())
+        nv.call('vtf_dedup_init', ptr(key), c_i64(N), stream())
+        nv.call('vtf_cosine_dedup_tc', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), c_int(rank), c_int(world),
+                ptr(key), stream())
+        nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
+        return key
+
     def hash_dedup(self, bits, rank, world):
         """bits: int64 [N,64] of 0/1 -> packed (distance, argmin) keys, int64 [N]."""
         N = bits.shape[0]
