@@ -209,12 +209,20 @@ def main():
     sweeps = [(a.elapsed_time(b), flops) for (name, a, b, flops) in eng.events if name == 'sil_sweep']
     pk = peaks()
     roof = None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the sweep from the committed ncu --set full capture
+        with open(osp.join(ROOT, 'profiles', 'r01_sweep_ncu_summary.json')) as f:
+            ncu = json.load(f)
+        if ncu['rows'] == N and ncu['dim'] == d and world == 1:
+            traffic = ncu['traffic_bytes_per_launch']
+    except Exception:  # noqa: BLE001
+        pass
     if sweeps:
         t_ms = float(np.mean([t for t, _ in sweeps]))
         flops = sweeps[0][1]
         ach = flops / (t_ms * 1e-3) / 1e12
         roof = dict(bound='tensor', kernel='sil_sweep_kernel (tcgen05 kind::f16, fp32 accumulate)', achieved=ach,
-                    peak=pk['tf_sust'], unit='TFLOP/s', frac=ach / pk['tf_sust'], traffic=None, ms_per_launch=t_ms,
+                    peak=pk['tf_sust'], unit='TFLOP/s', frac=ach / pk['tf_sust'], traffic=traffic, ms_per_launch=t_ms,
                     flop_per_launch=flops, share_of_step=t_ms * len(sweeps) / args.steps / ms_step,
                     peak_source=pk['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)')
     phases = {}

@@ -217,6 +217,10 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             int cur_cell = -1;
             for (int t = t0; t < t1; ++t) {
+                // the four cell ids of this warp's half tile, requested before the accumulator wait
+#if VTF_CELL_PREFETCH
+                const int4 cells = __ldg(reinterpret_cast<const int4*>(prm.chunk_cell + ((int64_t)t * BN + half * 128) / 32));
+#endif
                 mbar_wait(tfull_bar(as), acc_ph);
                 tc_fence_after();
 #pragma unroll 1
@@ -225,7 +229,11 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (uint32_t)(as * BN + half * 128 + c * 32) + ((uint32_t)(q * 32) << 16);
                     VTF_TMEM_LD32(taddr, v);
+#if VTF_CELL_PREFETCH
+                    const int cell = c == 0 ? cells.x : (c == 1 ? cells.y : (c == 2 ? cells.z : cells.w));
+#else
                     const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
+#endif
                     if (cell != cur_cell) {
                         if (cur_cell >= 0)
                             atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);

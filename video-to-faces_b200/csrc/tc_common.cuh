@@ -4,6 +4,19 @@
 #include <cuda.h>
 #include "common.cuh"
 
+#ifndef VTF_ARRIVE_RELAXED
+#define VTF_ARRIVE_RELAXED 0   // A/B on one box: the relaxed remote arrive is 18% SLOWER (971 vs 825 ms per 1M sweep)
+#endif
+#ifndef VTF_CELL_PREFETCH
+#define VTF_CELL_PREFETCH 1
+#endif
+#ifndef VTF_WAIT_HINT_NS
+#define VTF_WAIT_HINT_NS 2000   // suspend-time hint of mbarrier.try_wait: fewer polls, less power, higher clock (-2.5%)
+#endif
+#ifndef VTF_TIMEOUT_EVERY
+#define VTF_TIMEOUT_EVERY 1      // read clock64() for the hang watchdog every n-th failed poll
+#endif
+
 namespace vtf {
 namespace tc {
 
@@ -28,16 +41,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
+    uint32_t done = 0, polls = 0;
     const unsigned long long t0 = clock64();
     while (true) {
+#if VTF_WAIT_HINT_NS > 0
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)VTF_WAIT_HINT_NS) : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
         if (done) return;
-        if (clock64() - t0 > kTimeoutCycles) __trap();   // a broken pipeline must not hang the device
+        if ((++polls % VTF_TIMEOUT_EVERY) == 0 && clock64() - t0 > kTimeoutCycles) __trap();   // a broken pipeline must not hang the device
     }
 }
 
@@ -57,12 +78,18 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster (cutlass ClusterBarrier::arrive form: no
+// .release.cluster -- that qualifier costs a full membar (ERRBAR) per arrive, 24% of the epilogue samples, and the
+// only thing ordered here is TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+#if VTF_ARRIVE_RELAXED
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+#else
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+#endif
         ::"r"(bar), "r"(cta) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // cute::Sm100MmaPeerBitMask: address of the same barrier in the even CTA

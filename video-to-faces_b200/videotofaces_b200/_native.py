@@ -9,7 +9,7 @@ import os.path as osp
 
 c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
-LIB_PATH = osp.join(osp.dirname(osp.abspath(__file__)), '_lib', 'libvtf_b200.so')
+LIB_PATH = os.environ.get('VTF_LIB') or osp.join(osp.dirname(osp.abspath(__file__)), '_lib', 'libvtf_b200.so')   # VTF_LIB: A/B builds
 
 # name -> (restype, argtypes); mirrors include/vtf_b200.h one to one (tests/test_cabi.py checks it)
 SIGNATURES = {
