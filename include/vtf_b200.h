@@ -67,6 +67,11 @@ int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T,
  * when thr[t] is not reached inside this shard.                                            */
 int vtf_kpp_pick(const float* closest, int64_t N, const float* thr, int T,
                  const float* offset_in, float* total_out, int64_t* idx, void* stream);
+/* The same result from the plain one-thread chain (N dependent fp32 adds).  vtf_kpp_pick reproduces that chain
+ * bit for bit with block-wide integer prefix sums inside each binade of the running sum and falls back to single
+ * steps only at ties, binade changes and oversized addends; this entry point is the cross-check.  */
+int vtf_kpp_pick_serial(const float* closest, int64_t N, const float* thr, int T,
+                        const float* offset_in, float* total_out, int64_t* idx, void* stream);
 
 /* ---- a6: Lloyd iteration (SK/cluster/_k_means_lloyd.pyx:23-218) ---------------------------
  * assign: labels[i] = argmin_c (|c|^2 - 2 x_i.c), fp32, first index on ties (:205-213);

@@ -80,6 +80,44 @@ def test_kpp_pick_is_the_sequential_fp32_cumsum(K, N):
     assert np.array_equal(got, want)                          # bit-exact: same additions in the same order
 
 
+def _adversarial_sequences():
+    rng = np.random.default_rng(0)
+    out = {}
+    out['uniform_1m'] = (rng.random(1_000_003, dtype=np.float32) * 2).astype(np.float32)
+    # exact ties at many scales: multiples of 2^-k collide with the half-ulp of the running sum again and again
+    out['ties'] = (rng.integers(0, 64, 300_000) * np.float32(2.0 ** -7)).astype(np.float32)
+    out['ties_small'] = (rng.integers(0, 3, 200_000) * np.float32(0.5)).astype(np.float32)
+    z = (rng.random(100_000, dtype=np.float32)).astype(np.float32)
+    z[rng.random(100_000) < 0.7] = 0.0
+    z[:5000] = 0.0                                           # leading zeros: the sum stays 0
+    out['zeros'] = z
+    big = rng.random(50_000, dtype=np.float32).astype(np.float32)
+    big[::997] *= np.float32(1e6)                            # addends far larger than the running sum
+    out['jumps'] = big
+    out['wide_range'] = np.exp(rng.uniform(-60, 20, 120_000)).astype(np.float32)
+    out['tiny'] = (rng.random(30_000, dtype=np.float32) * np.float32(1e-38)).astype(np.float32)
+    out['kmeans_like'] = (rng.standard_normal(400_000).astype(np.float32) ** 2 * np.float32(0.8) + np.float32(0.3)).astype(np.float32)
+    return out
+
+
+@pytest.mark.parametrize('name', ['uniform_1m', 'ties', 'ties_small', 'zeros', 'jumps', 'wide_range', 'tiny', 'kmeans_like'])
+def test_kpp_pick_parallel_scan_is_bit_exact(K, name):
+    """The block-scan pick must reproduce numpy's sequential fp32 cumsum bit for bit -- final sum and every
+    searchsorted position -- on sequences built to hit ties, binade changes, zeros and oversized addends."""
+    v = _adversarial_sequences()[name]
+    cs = np.cumsum(v)                                        # sequential fp32
+    rng = np.random.default_rng(1)
+    thr = np.sort((rng.random(7) * float(cs[-1])).astype(np.float32))
+    thr[0] = cs[len(cs) // 3]                                # exactly equal to a prefix value: side='left'
+    thr = np.sort(thr)
+    want = np.searchsorted(cs, thr, side='left').astype(np.int64)
+    want[want >= v.size] = -1
+    for serial in (True, False):
+        idx, total = K.kpp_pick(dev(v), dev(thr), serial=serial, want_total=True)
+        assert np.array_equal(idx.cpu().numpy(), want), ('serial' if serial else 'scan', name)
+        assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), ('serial' if serial else 'scan', name)
+
+
 @pytest.mark.parametrize('N,d,k', [(5000, 512, 6), (3001, 768, 3), (1000, 1024, 32), (33, 64, 2), (2000, 20, 4), (600, 1024, 60)])
 def test_lloyd_assign_and_sums(K, N, d, k):
     X = blobs(N, d, kc=min(k, 8), seed=11, normalize=(d == 512))

@@ -79,7 +79,8 @@ def main():
     add('col_stats', lambda: K.col_stats(X), B)
     add('center_rows', lambda: K.center_rows(X, mean), 2 * B)
     add('kpp_dist T=3', lambda: K.kpp_dist(X, X[:3].contiguous(), closest), B + 3 * N * 4 + N * 4)
-    add('kpp_pick (sequential fp32 chain)', lambda: K.kpp_pick(closest, thr), N * 4)
+    add('kpp_pick (exact block scan)', lambda: K.kpp_pick(closest, thr), N * 4)
+    add('kpp_pick_serial (one-thread chain)', lambda: K.kpp_pick(closest, thr, serial=True), N * 4)
     add('lloyd_assign k=%d' % k, lambda: K.lloyd_assign(X, C, labels, counts, nch), B + N * 8, 2.0 * N * k * d)
     add('cluster_sums k=%d' % k, lambda: K.cluster_sums(X, labels, k), B + N * 4)
     add('cluster_dispersion k=%d' % k, lambda: K.cluster_dispersion(X, labels, C64), B + N * 4)

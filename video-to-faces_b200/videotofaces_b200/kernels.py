@@ -80,11 +80,13 @@ class CudaKernels:
                 ptr(ws), stream())
         return out, pots
 
-    def kpp_pick(self, closest, thr32):
+    def kpp_pick(self, closest, thr32, serial=False, want_total=False):
         T = thr32.numel()
         idx = self.empty((T,), torch.int64)
-        nv.call('vtf_kpp_pick', ptr(closest), c_i64(closest.numel()), ptr(thr32), c_int(T), None, None, ptr(idx), stream())
-        return idx
+        total = self.empty((1,), torch.float32) if want_total else None
+        nv.call('vtf_kpp_pick_serial' if serial else 'vtf_kpp_pick', ptr(closest), c_i64(closest.numel()), ptr(thr32), c_int(T),
+                None, ptr(total), ptr(idx), stream())
+        return (idx, total) if want_total else idx
 
     # ------------------------------------------------------------------ a6
     def lloyd_assign(self, Xc, C, labels, counts, n_changed):
