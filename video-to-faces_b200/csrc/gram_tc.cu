@@ -8,17 +8,28 @@
 //
 // Layout (DESIGN.md "silhouette sweep"):
 //   Xh   [P, d] fp16, rows permuted so that every 32-column chunk belongs to one "cell" (= one joint
-//        label tuple over all labellings), zero rows as padding, values scaled by a power of two.
-//   sqn  [P]    fp32 squared norms of the rounded rows (padding: -1e30 so the clamp removes it).
-//   cellsum [n_cells, P] fp32: sum over the columns of a cell of sqrt(max(n_p + n_q - 2 x_p.x_q, 0)).
+//        label tuple over all labellings), zero rows as padding, values scaled by a power of two s.
+//   aug  [2][P][16] fp16 (silhouette.cu, store_aug): the half squared norms m = |Xh_p|^2 / 2 as three fp16
+//        pieces against a constant, so that ONE extra K=16 MMA per tile turns the Gram accumulator into
+//        T = Xh_p.Xh_q - m_p - m_q = -s^2 D^2 / 2.  The norms ride in the MMA: the epilogue needs no loads.
+//   cellsum [n_cells, P] fp32: per row, the sum over the columns of a cell of sqrt(max(-T, 0)) * sqrt(2)/s.
 //
-// One CTA per SM (persistent).  Work item = 128-row block x column segment.  Roles:
-//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
-//   warp 1      MMA issuer     (one lane; tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accum in TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld 32x32b.x32 -> fma/max/sqrt.approx/add in registers)
-// The 128 x d A block of the item stays resident in shared memory (d <= 512) so only B streams; the
-// accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
-// MMAs of tile t+1.  Algorithmic flops 2*P^2*d per sweep; tensor-bound.
+// Persistent, one CTA per SM, CTA PAIRS (cta_group::2) by default: the pair runs one 256 x 256 MMA tile,
+// each CTA keeps its own 128 x d A block resident in shared memory (d <= 512) and streams only HALF of
+// every B k-block (16 KB), 6 ring stages; both accumulator halves are double-buffered in TMEM (2 x 256
+// columns) so the epilogue of tile t overlaps the MMAs of tile t+1.  Roles per CTA:
+//   warp 0      TMA producer   (cp.async.bulk.tensor...cta_group::2, 128B swizzle, complete_tx on the
+//                               leader's mbarrier; the augmented block travels in the same ring)
+//   warp 1      MMA issuer     (leader CTA, one lane; tcgen05.mma.cta_group::2.kind::f16, M=256 N=256
+//                               K=16, fp32 accumulate in TMEM; multicast tcgen05.commit frees stages and
+//                               publishes accumulators in both CTAs)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b.x32 -> max / sqrt.approx / add, 3 ALU ops per element,
+//                               one RED.F32 per cell change; D_pp = 0 on the diagonal chunk)
+// Work unit = 256-row block x column segment (segments only when row blocks cannot fill the machine).
+// mbarrier waits carry a suspend-time hint (less polling = less power = higher clock under the 1 kW cap)
+// and a 3 s clock64 watchdog that traps instead of hanging the device.
+// Measured: 1M x 512 in 751-805 ms = 1270-1364 TFLOP/s (0.91-0.98 of the measured sustained bf16 peak);
+// history of variants and same-box A/B numbers in DESIGN.md.  Algorithmic flops 2*P^2*d; tensor-bound.
 #include <stdlib.h>
 #include "tc_common.cuh"
 

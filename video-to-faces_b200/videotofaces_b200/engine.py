@@ -88,6 +88,23 @@ class GroupingEngine:
         A = np.ascontiguousarray(A, dtype={torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64}[dtype])
         return torch.from_numpy(A).to(self.device, non_blocking=False)
 
+    def upload_replicated(self, A):
+        """Host matrix -> the same full matrix on every rank.  With several ranks each one uploads only its row
+        shard over its own PCIe link and the shards are all-gathered over NVLink (2 GB: ~3 ms at 8 GPUs) instead
+        of every rank pulling the whole matrix through the host ('NCCL scatter')."""
+        if isinstance(A, torch.Tensor) and A.is_cuda:
+            return A.to(device=self.device, dtype=torch.float32).contiguous()
+        if not self.comm.active:
+            return self.to_device(A)
+        A = A if isinstance(A, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(A, dtype=np.float32))
+        n = A.shape[0]
+        bounds = self._bounds(n)
+        b, e = bounds[self.comm.rank], bounds[self.comm.rank + 1]
+        full = torch.empty(A.shape, dtype=torch.float32, device=self.device)
+        full[b:e].copy_(A[b:e], non_blocking=True)
+        self.comm.allgather_rows(full, bounds)
+        return full
+
     def _bounds(self, n, align=1):
         return shard_bounds(n, self.comm.world, align)
 
@@ -167,7 +184,7 @@ class GroupingEngine:
 
     # ------------------------------------------------------------------------------ a6 prologue
     def prepare(self, X):
-        X = self.to_device(X)
+        X = self.upload_replicated(X)
         with self.span('prepare'):
             return self._prepare(X)
 
