@@ -138,6 +138,25 @@ def test_cluster_faces_golden(tmp_path, golden_dir, capsys, name):
     assert 'Grouped %u images into %s folders:' % (X.shape[0], '/'.join(str(k) for k in ks)) in out
 
 
+@pytest.mark.parametrize('N,d', [(500, 100), (5000, 72), (300, 20)])
+def test_unaligned_dimension_and_odd_sizes(engine, N, d):
+    """Feature dimensions that are not multiples of 16/64 (padded with zero columns) through every entry."""
+    X = blobs(N, d, kc=4, noise=1.0, seed=2, normalize=False)
+    ctx, res = engine.kmeans_sweep(X, [2, 3], 0)
+    scores = engine.cluster_scores(ctx, res)
+    ref = RC.cluster_core(X, [2, 3], 0, inits=[X[r.seeds] for r in res])
+    for r, lab, cen, sc, rsc in zip(res, ref['labels'], ref['centers'], scores, ref['scores']):
+        assert (r.labels.cpu().numpy() == lab).mean() >= 0.999 and tuple(r.centers.shape) == cen.shape
+        np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-4)
+    Xd = plant_dupes(X, frac=10, seed=1, normalize=False)[0]
+    assert np.array_equal(engine.dedup(Xd, 0.2)[2], RC.dedup_core(Xd, 0.2)[2])
+    assert np.array_equal(engine.dedup(Xd, 0.2, force='tc')[2], RC.dedup_core(Xd, 0.2)[2])
+    tc = engine.silhouette_scores(ctx, [r.labels for r in res], [2, 3], force='tc')
+    np.testing.assert_allclose(tc, [s[1] for s in ref['scores']], rtol=2e-4)
+    assert tuple(engine.delete_rows(Xd, np.array([1, 5])).shape) == (N - 2, d)
+    assert np.array_equal(engine.classify(X[:100], X[200:205], 0.6)[1], RC.classify_core(X[:100], X[200:205], 5, 0.6)[1])
+
+
 def test_four_rows_error_like_reference(tmp_path):
     X = blobs(4, 512, kc=2, noise=0.5, seed=0)
     paths = fake_faces(str(tmp_path), 4)

@@ -109,6 +109,22 @@ def test_hash_dedup_decode(eng):
     assert mins.dtype == np.uint16 and np.array_equal(mins, rmins) and np.array_equal(inds, rinds) and np.array_equal(idx, ridx)
 
 
+def test_unaligned_feature_dimension(eng):
+    """d = 100: the engine pads to 112 zero columns; labels, centres (sliced back) and scores are the oracle's."""
+    X = blobs(400, 100, kc=4, noise=1.0, seed=2, normalize=False)
+    ctx, res = eng.kmeans_sweep(X, [2, 3], 0)
+    ref = RC.cluster_core(X, [2, 3], 0)
+    scores = eng.cluster_scores(ctx, res)
+    for r, lab, cen, sc, rsc in zip(res, ref['labels'], ref['centers'], scores, ref['scores']):
+        assert np.array_equal(r.labels.numpy(), lab) and r.centers.shape == cen.shape
+        np.testing.assert_allclose(r.centers.numpy(), cen, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-4)
+    Xd = plant_dupes(X, frac=10, seed=1, normalize=False)[0]
+    assert np.array_equal(eng.dedup(Xd, 0.2)[2], RC.dedup_core(Xd, 0.2)[2])
+    assert eng.delete_rows(Xd, np.array([1, 5])).shape == (398, 100)
+    assert np.array_equal(eng.classify(X[:100], X[200:205], 0.6)[1], RC.classify_core(X[:100], X[200:205], 5, 0.6)[1])
+
+
 def test_four_rows_fail_like_the_reference(eng):
     X = blobs(4, 512, kc=2, noise=0.5, seed=0)
     ctx, res = eng.kmeans_sweep(X, [2, 3, 4], 0)

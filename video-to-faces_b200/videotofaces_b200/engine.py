@@ -33,7 +33,7 @@ class KMeansResult:
 
 class FitContext:
     """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
-    __slots__ = ('X', 'Xc', 'N', 'd', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol')
+    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol')
 
 
 def n_local_trials(k):
@@ -105,6 +105,15 @@ class GroupingEngine:
         self.comm.allgather_rows(full, bounds)
         return full
 
+    @staticmethod
+    def _pad16(X, mult=16):
+        """Zero columns up to a multiple of 16 (64 for the tensor-core kernels): dot products, norms and distances
+        are unchanged, and every kernel can rely on 128-bit loads / whole k-blocks (FaceNet 512, ViT 768/1024 are
+        already aligned)."""
+        d = X.shape[1]
+        pad = (-d) % mult
+        return X if pad == 0 else torch.nn.functional.pad(X, (0, pad)).contiguous()
+
     def _bounds(self, n, align=1):
         return shard_bounds(n, self.comm.world, align)
 
@@ -114,14 +123,16 @@ class GroupingEngine:
         Large inputs run on the tensor cores (split-fp16, fp32-GEMM accuracy), small ones on the fp32 pipe;
         `force` = 'tc' | 'simt' overrides the choice."""
         X = self.to_device(X)
-        N, d = X.shape
+        N = X.shape[0]
         if N == 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64)
-        Xn = self.K.normalize_rows(X)
-        tc_ok = d % 64 == 0 and 64 <= d <= 4096 and hasattr(self.K, 'cosine_dedup_tc')
+        tc_ok = X.shape[1] <= 4096 and hasattr(self.K, 'cosine_dedup_tc')
         use_tc = (tc_ok and N >= TC_DEDUP_MIN_ROWS) if force is None else (force == 'tc')
         if use_tc and not tc_ok:
-            raise ValueError('tensor-core dedup needs d % 64 == 0')
+            raise ValueError('tensor-core dedup needs d <= 4096')
+        X = self._pad16(X, 64 if use_tc else 16)
+        d = X.shape[1]
+        Xn = self.K.normalize_rows(X)
         with self.span('dedup', flops=float(N) * N * d):
             key = (self.K.cosine_dedup_tc if use_tc else self.K.cosine_dedup)(Xn, self.comm.rank, self.comm.world)
         self.comm.allreduce_min(key)
@@ -150,16 +161,17 @@ class GroupingEngine:
     def delete_rows(self, X, idx):
         """np.delete(X, idx, axis=0) (dupes.py:68) on the device; returns a device tensor."""
         X = self.to_device(X)
+        d = X.shape[1]
         keep = np.ones(X.shape[0], dtype=bool)
         keep[idx] = False
         kept = torch.from_numpy(np.nonzero(keep)[0].astype(np.int64)).to(self.device)
-        return self.K.gather_rows(X, kept)
+        return self.K.gather_rows(self._pad16(X), kept)[:, :d].contiguous()
 
     # ------------------------------------------------------------------------------ a3 classify
     def classify(self, X, R, thr):
         """grouping.py:51-56.  Returns (dist fp32 [N,R], inds int64 [N]) as numpy."""
-        X = self.to_device(X)
-        R = self.to_device(R)
+        X = self._pad16(self.to_device(X))
+        R = self._pad16(self.to_device(R))
         Xn = self.K.normalize_rows(X)
         Rn = self.K.normalize_rows(R)
         b, e = self._my_rows(X.shape[0])
@@ -185,8 +197,12 @@ class GroupingEngine:
     # ------------------------------------------------------------------------------ a6 prologue
     def prepare(self, X):
         X = self.upload_replicated(X)
+        d_orig = X.shape[1]
         with self.span('prepare'):
-            return self._prepare(X)
+            ctx = self._prepare(self._pad16(X, 64 if X.shape[0] >= TC_MIN_ROWS and X.shape[1] <= 1024 else 16))
+        ctx.d_orig = d_orig
+        ctx.tol /= d_orig                  # mean over the real columns: zero padding adds no variance
+        return ctx
 
     def _prepare(self, X):
         ctx = FitContext()
@@ -201,7 +217,7 @@ class GroupingEngine:
         ctx.mean64 = s / ctx.N
         ctx.mean32 = ctx.mean64.to(torch.float32)
         var = q / ctx.N - ctx.mean64 * ctx.mean64                              # np.var(X, axis=0), _kmeans.py:292
-        ctx.tol = float(var.clamp_min(0).mean().item()) * 1e-4                 # _kmeans.py:293, tol=1e-4
+        ctx.tol = float(var.clamp_min(0).sum().item()) * 1e-4                  # _kmeans.py:293 (mean taken in prepare())
         ctx.Xc = self.K.center_rows(X, ctx.mean32)                             # _kmeans.py:1487-1490
         return ctx
 
@@ -291,7 +307,7 @@ class GroupingEngine:
         comm.allreduce_sum(sq)
         comm.allgather_rows(labels, ctx.bounds)
         inertia = float(sq.sum().item())
-        centers = (C + ctx.mean32).contiguous()                                # _kmeans.py:1543-1546
+        centers = (C + ctx.mean32)[:, :ctx.d_orig].contiguous()                # _kmeans.py:1543-1546
         return KMeansResult(k=k, labels=labels, centers=centers, inertia=inertia, n_iter=n_iter,
                             counts=counts, strict=strict)
 
@@ -342,7 +358,7 @@ class GroupingEngine:
                 C0 = self.K.gather_rows(ctx.Xc, torch.from_numpy(seeds).to(self.device))
             else:
                 seeds = None
-                C0 = (self.to_device(inits[j]) - ctx.mean32).contiguous()
+                C0 = (self._pad16(self.to_device(inits[j])) - ctx.mean32).contiguous()
             with self.span('lloyd'):
                 res = self.lloyd(ctx, C0)
             res.seeds = seeds
@@ -399,10 +415,10 @@ class GroupingEngine:
         for c in counts_list:
             self._check_n_labels(int((c > 0).sum().item()), ctx.N)
         d = ctx.d
-        tc_ok = (d % 64 == 0 and 64 <= d <= 1024)
-        use_tc = tc_ok and ctx.N >= TC_MIN_ROWS if force is None else (force == 'tc')
+        tc_ok = d <= 1024
+        use_tc = (tc_ok and ctx.N >= TC_MIN_ROWS) if force is None else (force == 'tc')
         if use_tc and not tc_ok:
-            raise ValueError('tensor-core silhouette needs d % 64 == 0 and 64 <= d <= 1024')
+            raise ValueError('tensor-core silhouette needs d <= 1024')
         if use_tc:
             return self._silhouette_tc(ctx, labels_list, ks, counts_list)
         return self._silhouette_exact(ctx, labels_list, ks, counts_list)
@@ -478,12 +494,13 @@ class GroupingEngine:
             return (self._silhouette_tc(ctx, labels_list[:h], ks[:h], counts_list[:h]) +
                     self._silhouette_tc(ctx, labels_list[h:], ks[h:], counts_list[h:]))
         with self.span('sil_pack'):
-            scale, shift, pad_m = self.sil_scale(ctx.Xc)
-            Xh, aug = K.sil_pack(ctx.Xc, perm, P, scale, shift, pad_m)
+            Xc = self._pad16(ctx.Xc, 64)                                      # whole 64-column k-blocks
+            scale, shift, pad_m = self.sil_scale(Xc)
+            Xh, aug = K.sil_pack(Xc, perm, P, scale, shift, pad_m)
             cellsum = K.zeros((G, P), torch.float32)
         bounds = self._bounds(P // 128, 2)       # even row-block ranges: CTA pairs share one 256-row MMA
         rb0, rb1 = bounds[comm.rank], bounds[comm.rank + 1]
-        with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * ctx.d):
+        with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * Xc.shape[1]):
             K.sil_sweep(Xh, aug, scale, chunk_cell, G, rb0, rb1, cellsum)
         out = K.zeros((len(ks),), torch.float64)
         with self.span('sil_finish'):
