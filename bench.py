@@ -9,8 +9,9 @@ k = 2..6, silhouette + Calinski-Harabasz + Davies-Bouldin for every k, selection
   value   X already resident in HBM, CUDA events around the step, max over ranks
   e2e     the public API call on a pinned HOST matrix: H2D of X and D2H of labels/scores inside the
           timed region (videotofaces_b200.grouping.cluster_labels)
-  roofline  the tcgen05 silhouette sweep: 2*P^2*d flop per launch / its CUDA-event time, against the
-          measured dense bf16 peak of MEASURED_PEAKS.json (kind::f16 runs at the bf16 rate)
+  roofline  the tcgen05 silhouette sweep: the MMA flops it executes per launch (upper triangle of the Gram
+          matrix: ~P^2*d, the distance matrix is symmetric) / its CUDA-event time, against the measured dense
+          bf16 peak of MEASURED_PEAKS.json (kind::f16 runs at the bf16 rate)
   cpu_baseline  the reference's own sklearn call sequence (oracle/reference_calls.py) on a bounded
           row sample, timed on this box's host cores (rank 0, N=1 only)
 
@@ -221,9 +222,13 @@ def main():
         t_ms = float(np.mean([t for t, _ in sweeps]))
         flops = sweeps[0][1]
         ach = flops / (t_ms * 1e-3) / 1e12
-        roof = dict(bound='tensor', kernel='sil_sweep_kernel (tcgen05 kind::f16, fp32 accumulate)', achieved=ach,
+        full_gram = 2.0 * float(((N + 255) // 256) * 256) ** 2 * d
+        roof = dict(bound='tensor', kernel='sil_sweep_kernel (tcgen05 cta_group::2 kind::f16, fp32 accumulate in TMEM)', achieved=ach,
                     peak=pk['tf_sust'], unit='TFLOP/s', frac=ach / pk['tf_sust'], traffic=traffic, ms_per_launch=t_ms,
                     flop_per_launch=flops, share_of_step=t_ms * len(sweeps) / args.steps / ms_step,
+                    note=('flop_per_launch counts the MMAs the kernel EXECUTES: D is symmetric, so only tiles on or above the diagonal '
+                          'are computed (%.3f of the full Gram %.4g flop that SURVEY 8d lists); achieved/peak is the tensor-pipe figure'
+                          % (flops * world / full_gram, full_gram)) if flops * world < 0.75 * full_gram else 'full Gram sweep',
                     peak_source=pk['source'] + ' bf16_tflops_sustained (kernel timed inside a long step)')
     phases = {}
     for name, a, b, _ in eng.events:

@@ -172,6 +172,13 @@ int vtf_absmax(const float* X, int64_t N, int d, float* out, void* stream);
 int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, float scale,
                   const int32_t* chunk_cell, int n_cells, int64_t rb_begin, int64_t rb_end,
                   float* cellsum, void* stream);
+/* Symmetric form (D_pq = D_qp): only tiles on or above the diagonal are computed -- half the MMAs -- and every
+ * off-diagonal block also feeds the row sums of its columns (warp transpose-reduce in the epilogue).  Rank r of
+ * `world` sweeps unit pairs (q, U-1-q), q = r, r + world, ... (U = P/256 units of 256 rows); each rank's cellsum
+ * then holds partial sums for ALL rows and the caller adds them (all-reduce) before vtf_sil_finish_cells.     */
+int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int d, float scale,
+                      const int32_t* chunk_cell, int n_cells, int rank, int world,
+                      float* cellsum, void* stream);
 /* finish: for labelling l (k_l clusters), per real row: a = S_own/(n_own-1),
  * b = min_{c != own} S_c/n_c, s = (b-a)/max(a,b) (0 for singleton clusters, :323), and
  * out[l] += sum_i s_i in fp64.  From the exact path: vtf_sil_finish_rows on rowsum[N,k].    */

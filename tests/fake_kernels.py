@@ -184,6 +184,29 @@ class FakeKernels:
         for c in range(n_cells):
             cellsum[c, rows[0]:rows[-1] + 1] += torch.from_numpy(D[:, cc == c].sum(1, dtype=np.float32))
 
+    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum):
+        """Upper-triangle sweep: unit pairs (q, U-1-q) of 256 rows; off-diagonal tiles feed rows and columns."""
+        f = _np(Xh).astype(np.float32)
+        m = _np(aug)
+        cc = np.repeat(_np(chunk_cell), 32)
+        P = f.shape[0]
+        U = P // 256
+        out = np.zeros((n_cells, P), dtype=np.float64)
+        for q in range(rank, (U + 1) // 2, world):
+            for u in sorted({q, U - 1 - q}):
+                rows = np.arange(u * 256, (u + 1) * 256)
+                for t in range(u, U):
+                    cols = np.arange(t * 256, (t + 1) * 256)
+                    T = f[rows] @ f[cols].T - m[rows][:, None] - m[cols][None, :]
+                    D = np.sqrt(np.maximum(-T, 0)) * (np.sqrt(2.0) / scale)
+                    if t == u:
+                        np.fill_diagonal(D, 0.0)
+                    for c in range(n_cells):
+                        out[c, rows] += D[:, cc[cols] == c].sum(1)
+                        if t != u:
+                            out[c, cols] += D[cc[rows] == c, :].sum(0)
+        cellsum += torch.from_numpy(out.astype(np.float32))
+
     def sil_finish_cells(self, cellsum, cell_to_cluster, k, perm, labels, counts, p_begin, p_end, out_slot):
         cs, c2c, pm, lab, cnt = _np(cellsum), _np(cell_to_cluster), _np(perm), _np(labels), _np(counts)
         tot = 0.0

@@ -40,6 +40,10 @@ def _worker(rank, world, port, out):
         ctx, res = eng.kmeans_sweep(X, ks, 0)
         exact = eng.cluster_scores(ctx, res, force='exact')
         tc = eng.silhouette_scores(ctx, [r.labels for r in res], ks, [r.counts for r in res], force='tc')
+        eng.sym = True
+        tc_sym = eng.silhouette_scores(ctx, [r.labels for r in res], ks, [r.counts for r in res], force='tc')
+        eng.sym = None
+        assert np.allclose(tc_sym, tc, rtol=1e-6), (tc_sym, tc)
         Xd = plant_dupes(X, frac=10, seed=1)[0]
         mins, inds, idx = eng.dedup(Xd, 0.2)
         dist_m, lab = eng.classify(X[:300], X[300:310], 0.5)

@@ -236,6 +236,24 @@ def test_tensor_core_sweep_matches_exact_rowsums(engine, N, d, ks):
         assert rel.max() < 2e-5, rel                              # no systematic bias
 
 
+@pytest.mark.parametrize('N,d,ks', [(700, 64, [2, 3]), (3000, 512, [2, 3, 4, 5, 6]), (1500, 768, [2, 4]), (1100, 1024, [3]), (10000, 512, [2, 6])])
+def test_symmetric_sweep_matches_full_sweep(engine, N, d, ks):
+    """Upper-triangle sweep (row sums + transposed column sums) against the full sweep and the oracle."""
+    X = blobs(N, d, kc=4, seed=9, normalize=(d == 512))
+    ctx = engine.prepare(X)
+    rng = np.random.default_rng(0)
+    labels = [dev(rng.integers(0, k, N).astype(np.int32)) for k in ks]
+    engine.sym = False
+    full = engine.silhouette_scores(ctx, labels, ks, force='tc')
+    engine.sym = True
+    sym = engine.silhouette_scores(ctx, labels, ks, force='tc')
+    engine.sym = None
+    np.testing.assert_allclose(sym, full, rtol=2e-5, atol=2e-6)
+    if N <= 3000:
+        want = [RC.cluster_scores(X, l.cpu().numpy())[0] for l in labels]
+        np.testing.assert_allclose(sym, want, rtol=1e-4, atol=2e-6)
+
+
 def test_sweep_rejects_bad_shapes(K):
     from videotofaces_b200 import _native
     with pytest.raises(_native.NativeError):

@@ -69,6 +69,10 @@ def test_cells_layout_and_tc_path_agree_with_exact(eng):
         assert np.array_equal(c2c[j].numpy()[cc[live]], lab.numpy()[pm[live]])
     exact = eng.silhouette_scores(ctx, labels, ks, force='exact')
     tc = eng.silhouette_scores(ctx, labels, ks, force='tc')
+    eng.sym = True
+    tc_sym = eng.silhouette_scores(ctx, labels, ks, force='tc')
+    eng.sym = None
+    np.testing.assert_allclose(tc_sym, tc, rtol=1e-6)
     ref = [RC.cluster_scores(X, l.numpy())[0] for l in labels]
     np.testing.assert_allclose(exact, ref, rtol=1e-5)
     np.testing.assert_allclose(tc, ref, rtol=1e-4)

@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--rows', type=int, default=1_000_000)
     ap.add_argument('--dim', type=int, default=512)
     ap.add_argument('--reps', type=int, default=3)
+    ap.add_argument('--sym', action='store_true', help='time vtf_sil_sweep_sym (upper triangle) instead of the full sweep')
     args = ap.parse_args()
     from videotofaces_b200.runtime import get_engine
     from videotofaces_b200._native import c_f32, c_i64, c_int, c_vp
@@ -50,12 +51,16 @@ def main():
     perm, chunk_cell, c2c, G, P = eng.build_cells(labels, ks)
     scale, shift, pad_m = eng.sil_scale(Xc)
     Xh, aug = K.sil_pack(Xc, perm, P, scale, shift, pad_m)
-    flops = 2.0 * P * P * d
+    U = P // 256
+    flops = 2.0 * P * P * d if not args.sym else 2.0 * 256 * 256 * d * (U * (U + 1) / 2)
     libs = []
     for path in args.libs:
         lib = ctypes.CDLL(osp.abspath(path))
         lib.vtf_sil_sweep.restype = c_int
         lib.vtf_sil_sweep.argtypes = [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]
+        if args.sym:
+            lib.vtf_sil_sweep_sym.restype = c_int
+            lib.vtf_sil_sweep_sym.argtypes = [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp]
         libs.append((osp.basename(path), lib))
     cellsum = torch.zeros((G, P), dtype=torch.float32, device='cuda')
     stream = c_vp(torch.cuda.current_stream().cuda_stream)
@@ -66,8 +71,12 @@ def main():
             cellsum.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            rc = lib.vtf_sil_sweep(Xh.data_ptr(), aug.data_ptr(), P, d, scale, chunk_cell.data_ptr(), G, 0, P // 128,
-                                   cellsum.data_ptr(), stream)
+            if args.sym:
+                rc = lib.vtf_sil_sweep_sym(Xh.data_ptr(), aug.data_ptr(), P, d, scale, chunk_cell.data_ptr(), G, 0, 1,
+                                           cellsum.data_ptr(), stream)
+            else:
+                rc = lib.vtf_sil_sweep(Xh.data_ptr(), aug.data_ptr(), P, d, scale, chunk_cell.data_ptr(), G, 0, P // 128,
+                                       cellsum.data_ptr(), stream)
             b.record()
             torch.cuda.synchronize()
             assert rc == 0, name

@@ -36,6 +36,15 @@
 namespace vtf {
 namespace tc {
 
+#ifndef VTF_EPI_WARPS
+#define VTF_EPI_WARPS 8    // same-box A/B: 8 beats 16 in both forms (full 736 vs 772 ms, symmetric 407 vs 424 ms)
+#endif
+constexpr int kEpiWarps = VTF_EPI_WARPS;                 // 8 or 16: warps that drain TMEM (4 lane quarters x column slices)
+constexpr int kSlices = kEpiWarps / 4;                   // column slices of the 256-wide tile
+constexpr int kChunksPerWarp = (BN / 32) / kSlices;      // 32-column chunks per warp per tile
+constexpr int kSweepThreads = 64 + 32 * kEpiWarps;
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "4 lane quarters x 2 or 4 column slices");
+
 struct Params {
     const int32_t* chunk_cell;
     float* cellsum;
@@ -47,7 +56,37 @@ struct Params {
     int tiles_per_seg;   // 256-column tiles per segment
     int n_tiles;         // P / 256
     float flush_scale;   // sqrt(2) / scale: sqrt(max(-T, 0)) * flush_scale is the distance
+    int sym_rank;        // SYM: this rank sweeps unit pairs q = sym_rank, sym_rank + sym_world, ...
+    int sym_world;
 };
+
+// Work list shared by the three warp roles (they must walk it identically).
+//   full sweep: item -> (row unit, column segment);  rbu = row unit (CPC row blocks), tiles [t0, t1)
+//   SYM (D is symmetric): only tiles on or above the diagonal are computed; a tile off the diagonal feeds the row
+//   sums of its rows AND, through a warp transpose-reduce, the row sums of its columns.  Unit u sweeps tiles
+//   u..U-1, so units are handed out in pairs (q, U-1-q) of constant total length U+1.
+template <bool PAIR, bool SYM>
+__device__ __forceinline__ bool next_work(const Params& prm, int64_t it, int64_t unit0, int64_t unit_stride,
+                                          int64_t& rbu, int& t0, int& t1) {
+    if (SYM) {
+        const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
+        const int64_t q = prm.sym_rank + (unit0 + (it >> 1) * unit_stride) * prm.sym_world;
+        if (q >= n_q) return false;
+        const int64_t u = (it & 1) ? U - 1 - q : q;
+        rbu = u;
+        if ((it & 1) && u == q) { t0 = t1 = 0; return true; }      // middle unit of an odd U: already done
+        t0 = (int)u; t1 = (int)U;
+        return true;
+    }
+    const int64_t n_items = (prm.n_rb / (PAIR ? 2 : 1)) * prm.n_seg;
+    const int64_t item = unit0 + it * unit_stride;
+    if (item >= n_items) return false;
+    rbu = item / prm.n_seg;
+    const int seg = (int)(item % prm.n_seg);
+    t0 = seg * prm.tiles_per_seg;
+    t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+    return true;
+}
 
 // A_RESIDENT: the item's 128 x d A block is loaded once and kept; otherwise A k-blocks stream with B.
 // PAIR: two CTAs of a cluster (one SM pair) run one cta_group::2 MMA of 256 rows x 256 columns: each
@@ -55,8 +94,8 @@ struct Params {
 // traffic (the limiter of the single-CTA form: 64 B/cycle/SM against ~42 B/cycle/SM of L2 bandwidth)
 // and the shared-memory write traffic.  CTA 0 issues the MMAs; barriers that both CTAs wait on are
 // signalled with multicast commits, the accumulator-drained barrier collects arrivals from both.
-template <bool A_RESIDENT, int STAGES, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool A_RESIDENT, int STAGES, bool PAIR, bool SYM>
+__global__ void __launch_bounds__(kSweepThreads, 1)
 sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_aug_a, const __grid_constant__ CUtensorMap map_aug_b, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -88,7 +127,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * CPC); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * CPC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -106,7 +145,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int64_t n_items = (prm.n_rb / CPC) * prm.n_seg;     // work units: row block (pair) x column segment
+    static_assert(!SYM || PAIR, "the symmetric sweep runs on CTA pairs");
     const int64_t unit0 = blockIdx.x / CPC, unit_stride = gridDim.x / CPC;
 
     if (warp == 0) {
@@ -114,11 +153,11 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, a_ph = 0;
-            for (int64_t item = unit0; item < n_items; item += unit_stride) {
-                const int64_t rb = prm.rb_begin + CPC * (item / prm.n_seg) + cta_rank;
-                const int seg = (int)(item % prm.n_seg);
-                const int t0 = seg * prm.tiles_per_seg;
-                const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+            for (int64_t it = 0;; ++it) {
+                int64_t rbu; int t0, t1;
+                if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+                if (t0 >= t1) continue;
+                const int64_t rb = prm.rb_begin + CPC * rbu + cta_rank;
                 // PAIR: both CTAs load; every complete_tx lands on the LEADER's barrier, which expects both halves
                 if (A_RESIDENT) {
                     mbar_wait(a_empty, a_ph ^ 1u);
@@ -166,10 +205,10 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0 && leader) {
             int s = 0, as = 0;
             uint32_t ph = 0, a_ph = 0, acc_ph = 0;
-            for (int64_t item = unit0; item < n_items; item += unit_stride) {
-                const int seg = (int)(item % prm.n_seg);
-                const int t0 = seg * prm.tiles_per_seg;
-                const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+            for (int64_t it = 0;; ++it) {
+                int64_t rbu; int t0, t1;
+                if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+                if (t0 >= t1) continue;
                 if (A_RESIDENT) { mbar_wait(a_full, a_ph); a_ph ^= 1u; }
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(tempty_bar(as), acc_ph ^ 1u);
@@ -215,33 +254,45 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
         // ------------------------------------------------------------------ epilogue (8 warps)
         const int q = warp & 3;                 // TMEM lane quarter this warp can read
-        const int half = (warp - 2) >> 2;       // which 128 columns of the 256-wide tile
+        const int slice = (warp - 2) >> 2;      // which column slice of the 256-wide tile
+        constexpr int kSliceCols = BN / kSlices;
         int as = 0;
         uint32_t acc_ph = 0;
-        for (int64_t item = unit0; item < n_items; item += unit_stride) {
-            const int64_t rb = prm.rb_begin + CPC * (item / prm.n_seg) + cta_rank;
-            const int seg = (int)(item % prm.n_seg);
-            const int t0 = seg * prm.tiles_per_seg;
-            const int t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+        for (int64_t it = 0;; ++it) {
+            int64_t rbu; int t0, t1;
+            if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+            if (t0 >= t1) continue;
+            const int64_t rb = prm.rb_begin + CPC * rbu + cta_rank;
             const int64_t rowbase = rb * BM + q * 32;
             const int64_t p = rowbase + lane;
+            const int row_cell = SYM ? __ldg(prm.chunk_cell + (rowbase >> 5)) : 0;   // the cell of this warp's 32 rows
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             int cur_cell = -1;
             for (int t = t0; t < t1; ++t) {
                 // the four cell ids of this warp's half tile, requested before the accumulator wait
 #if VTF_CELL_PREFETCH
-                const int4 cells = __ldg(reinterpret_cast<const int4*>(prm.chunk_cell + ((int64_t)t * BN + half * 128) / 32));
+                int cells[kChunksPerWarp];
+                {
+                    const int32_t* cp = prm.chunk_cell + ((int64_t)t * BN + slice * kSliceCols) / 32;
+                    if (kChunksPerWarp == 4) {
+                        const int4 c4 = __ldg(reinterpret_cast<const int4*>(cp));
+                        cells[0] = c4.x; cells[1] = c4.y; cells[kChunksPerWarp - 2] = c4.z; cells[kChunksPerWarp - 1] = c4.w;
+                    } else {
+                        const int2 c2 = __ldg(reinterpret_cast<const int2*>(cp));
+                        cells[0] = c2.x; cells[1] = c2.y;
+                    }
+                }
 #endif
                 mbar_wait(tfull_bar(as), acc_ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int64_t col0 = (int64_t)t * BN + half * 128 + c * 32;
+#pragma unroll
+                for (int c = 0; c < kChunksPerWarp; ++c) {
+                    const int64_t col0 = (int64_t)t * BN + slice * kSliceCols + c * 32;
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + (uint32_t)(as * BN + half * 128 + c * 32) + ((uint32_t)(q * 32) << 16);
+                    const uint32_t taddr = tmem_base + (uint32_t)(as * BN + slice * kSliceCols + c * 32) + ((uint32_t)(q * 32) << 16);
                     VTF_TMEM_LD32(taddr, v);
 #if VTF_CELL_PREFETCH
-                    const int cell = c == 0 ? cells.x : (c == 1 ? cells.y : (c == 2 ? cells.z : cells.w));
+                    const int cell = cells[c];
 #else
                     const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
 #endif
@@ -254,25 +305,37 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     VTF_TMEM_WAIT(v);
                     // the accumulator holds T = s^2 (x_p.x_q - |x_p|^2/2 - |x_q|^2/2) = -s^2 D^2 / 2:
                     // distance = sqrt(max(-T, 0)) * sqrt(2)/s, the constant factor applied once per flush
-                    if (col0 != rowbase) {
+                    float r[32];
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            acc0 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 0]), 0.f));
-                            acc1 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 1]), 0.f));
-                            acc2 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 2]), 0.f));
-                            acc3 += sqrt_approx(fmaxf(-__uint_as_float(v[4 * j4 + 3]), 0.f));
-                        }
-                    } else {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
+                    for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
+                    if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float r = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
-                            acc0 += (j == lane) ? 0.f : r;
+                        for (int j = 0; j < 32; ++j) r[j] = (j == lane) ? 0.f : r[j];
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        acc0 += r[4 * j4 + 0]; acc1 += r[4 * j4 + 1]; acc2 += r[4 * j4 + 2]; acc3 += r[4 * j4 + 3];
+                    }
+                    if (SYM && t != (int)rbu) {
+                        // D_qp = D_pq: the same 32 x 32 block, summed over this warp's rows (all in cell row_cell), is
+                        // the contribution to the row sums of columns col0..col0+31.  Transpose-reduce: after the five
+                        // exchange steps lane l holds the column sum of column col0 + l.
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            const bool up = (lane & o) != 0;
+#pragma unroll
+                            for (int j = 0; j < o; ++j) {
+                                const float keep = up ? r[j + o] : r[j];
+                                const float send = up ? r[j] : r[j + o];
+                                r[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            }
                         }
+                        atomicAdd(prm.cellsum + (size_t)row_cell * prm.P + col0 + lane, r[0] * prm.flush_scale);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (PAIR) mbar_arrive_remote(tempty_bar(as), 0u); else mbar_arrive(tempty_bar(as)); }
+                if (lane == 0) { if (PAIR) mbar_arrive_remote<SYM>(tempty_bar(as), 0u); else mbar_arrive(tempty_bar(as)); }
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
             if (cur_cell >= 0)
@@ -308,16 +371,16 @@ static int make_aug_map(CUtensorMap* map, const void* aug, int64_t P, int groups
     return VTF_OK;
 }
 
-template <bool A_RES, int STAGES, bool PAIR>
+template <bool A_RES, int STAGES, bool PAIR, bool SYM>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& maa, const CUtensorMap& mab,
                   const Params& prm, int grid, void* stream) {
     const size_t stage = kBBlockBytes / (PAIR ? 2 : 1) + (A_RES ? 0 : kABlockBytes);
     const size_t smem = 1024 + (A_RES ? (size_t)prm.n_kb * kABlockBytes : 0) + STAGES * stage + 256;
-    auto kern = sil_sweep_kernel<A_RES, STAGES, PAIR>;
+    auto kern = sil_sweep_kernel<A_RES, STAGES, PAIR, SYM>;
     VTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "vtf_sil_sweep/smem");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kSweepThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -372,13 +435,49 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
     prm.tiles_per_seg = (prm.n_tiles + n_seg - 1) / n_seg;
     prm.n_seg = (prm.n_tiles + prm.tiles_per_seg - 1) / prm.tiles_per_seg;
     prm.flush_scale = 1.41421356237f / scale;
+    prm.sym_rank = 0; prm.sym_world = 1;
     const int64_t n_units = units * prm.n_seg;
     if (pair) {
         const int grid = 2 * (int)min(slots, n_units);
-        if (d <= 512) return tc::launch<true, 6, true>(ma, mb, maa, mab, prm, grid, stream);
-        return tc::launch<false, 6, true>(ma, mb, maa, mab, prm, grid, stream);
+        if (d <= 512) return tc::launch<true, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
+        return tc::launch<false, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
     }
     const int grid = (int)min(slots, n_units);
-    if (d <= 512) return tc::launch<true, 3, false>(ma, mb, maa, mab, prm, grid, stream);
-    return tc::launch<false, 4, false>(ma, mb, maa, mab, prm, grid, stream);
+    if (d <= 512) return tc::launch<true, 3, false, false>(ma, mb, maa, mab, prm, grid, stream);
+    return tc::launch<false, 4, false, false>(ma, mb, maa, mab, prm, grid, stream);
+}
+
+
+// Symmetric form: D_pq = D_qp, so only tiles on or above the diagonal are computed (half the MMAs, half the L2
+// traffic); every off-diagonal 32 x 32 block also feeds the row sums of its COLUMNS through a warp
+// transpose-reduce.  Each rank sweeps unit pairs (q, U-1-q), q = rank, rank + world, ...; its cellsum then holds
+// partial sums for ALL rows and the caller adds the ranks' arrays (all-reduce) before the finish pass.
+extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int d, float scale, const int32_t* chunk_cell,
+                                 int n_cells, int rank, int world, float* cellsum, void* stream) {
+    VTF_REQUIRE(Xh && aug && chunk_cell && cellsum && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0 &&
+                    n_cells > 0 && world > 0 && rank >= 0 && rank < world && scale > 0.f,
+                "vtf_sil_sweep_sym (P % 256 == 0, d % 64 == 0, 64 <= d <= 1024)");
+    int rc = vtf_device_check();
+    if (rc != VTF_OK) return rc;
+    CUtensorMap ma, mb, maa, mab;
+    if ((rc = tc::make_operand_map(&ma, Xh, P, d, tc::BM, "vtf_sil_sweep_sym")) != VTF_OK) return rc;
+    if ((rc = tc::make_operand_map(&mb, Xh, P, d, tc::BN / 2, "vtf_sil_sweep_sym")) != VTF_OK) return rc;
+    const __half* augA = (const __half*)aug;
+    const __half* augB = augA + (size_t)P * 16;
+    if ((rc = tc::make_aug_map(&maa, augA, P, tc::BM / 8)) != VTF_OK) return rc;
+    if ((rc = tc::make_aug_map(&mab, augB, P, (tc::BN / 2) / 8)) != VTF_OK) return rc;
+    tc::Params prm;
+    prm.chunk_cell = chunk_cell; prm.cellsum = cellsum; prm.P = P;
+    prm.rb_begin = 0; prm.n_rb = P / tc::BM;
+    prm.n_kb = d / tc::BK;
+    prm.n_tiles = (int)(P / tc::BN);
+    prm.n_seg = 1; prm.tiles_per_seg = prm.n_tiles;
+    prm.flush_scale = 1.41421356237f / scale;
+    prm.sym_rank = rank; prm.sym_world = world;
+    const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
+    if (rank >= n_q) return VTF_OK;
+    const int64_t mine = (n_q - rank + world - 1) / world;
+    const int grid = 2 * (int)min((int64_t)(num_sms() / 2), mine);
+    if (d <= 512) return tc::launch<true, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
+    return tc::launch<false, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
 }

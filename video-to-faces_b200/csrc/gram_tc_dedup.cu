@@ -180,7 +180,7 @@ dedup_sweep_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote(tempty_bar(as), 0u);
+                if (lane == 0) mbar_arrive_remote<false>(tempty_bar(as), 0u);
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
             if (i < prm.N && best < INFINITY)

@@ -4,9 +4,6 @@
 #include <cuda.h>
 #include "common.cuh"
 
-#ifndef VTF_ARRIVE_RELAXED
-#define VTF_ARRIVE_RELAXED 0   // A/B on one box: the relaxed remote arrive is 18% SLOWER (971 vs 825 ms per 1M sweep)
-#endif
 #ifndef VTF_CELL_PREFETCH
 #define VTF_CELL_PREFETCH 1
 #endif
@@ -78,19 +75,26 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster (cutlass ClusterBarrier::arrive form: no
-// .release.cluster -- that qualifier costs a full membar (ERRBAR) per arrive, 24% of the epilogue samples, and the
-// only thing ordered here is TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover)
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  RELAXED drops .release.cluster (the
+// cutlass ClusterBarrier::arrive form): the qualifier costs a membar (ERRBAR) per arrive, and the only thing ordered
+// here is TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover.  Which form is faster
+// is a power question and was settled by same-box A/B runs (tools/sweep_ab.py): the full sweep is 5% faster WITH
+// the membar (825 vs 971 ms before the wait hint existed), the symmetric sweep 10% faster WITHOUT it (407 vs 452 ms).
+template <bool RELAXED>
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-#if VTF_ARRIVE_RELAXED
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-#else
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-#endif
-        ::"r"(bar), "r"(cta) : "memory");
+    if (RELAXED) {
+        asm volatile(
+            "{\n\t.reg .b32 ra;\n\t"
+            "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+            "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+            ::"r"(bar), "r"(cta) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b32 ra;\n\t"
+            "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+            "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+            ::"r"(bar), "r"(cta) : "memory");
+    }
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // cute::Sm100MmaPeerBitMask: address of the same barrier in the even CTA
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {

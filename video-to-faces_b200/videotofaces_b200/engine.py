@@ -19,6 +19,7 @@ import torch
 from .dist import Comm, shard_bounds
 
 TC_MIN_ROWS = 4096        # below this the exact fp32 silhouette kernel is used (and is fast enough)
+TC_SYM_MIN_UNITS = 148    # symmetric (upper-triangle) sweep once there are at least 2 units of 256 rows per CTA pair
 TC_DEDUP_MIN_ROWS = 8192  # below this the fp32 FMA dedup kernel is used
 TC_MAX_CELLSUM_BYTES = 32 << 30
 
@@ -77,6 +78,7 @@ class GroupingEngine:
         self.device = kernels.device
         self.profile = False
         self.events = []
+        self.sym = None          # None: symmetric silhouette sweep for large inputs; True / False forces it
 
     def span(self, name, flops=0.0):
         return _Span(self, name, flops)
@@ -500,8 +502,20 @@ class GroupingEngine:
             cellsum = K.zeros((G, P), torch.float32)
         bounds = self._bounds(P // 128, 2)       # even row-block ranges: CTA pairs share one 256-row MMA
         rb0, rb1 = bounds[comm.rank], bounds[comm.rank + 1]
-        with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * Xc.shape[1]):
-            K.sil_sweep(Xh, aug, scale, chunk_cell, G, rb0, rb1, cellsum)
+        U = P // 256
+        sym = (U >= TC_SYM_MIN_UNITS * comm.world) if self.sym is None else bool(self.sym)
+        if sym:
+            # D is symmetric: sweep the tiles on or above the diagonal only; executed MMA flops = d * P^2 * (1 + 1/U)
+            n_q = (U + 1) // 2
+            mine = len(range(comm.rank, n_q, comm.world))
+            tiles = sum((U - q) + (q + 1 if U - 1 - q != q else 0) for q in range(comm.rank, n_q, comm.world))
+            with self.span('sil_sweep', flops=2.0 * tiles * 256 * 256 * Xc.shape[1]):
+                K.sil_sweep_sym(Xh, aug, scale, chunk_cell, G, comm.rank, comm.world, cellsum)
+            with self.span('sil_allreduce'):
+                comm.allreduce_sum(cellsum)
+        else:
+            with self.span('sil_sweep', flops=2.0 * (rb1 - rb0) * 128 * P * Xc.shape[1]):
+                K.sil_sweep(Xh, aug, scale, chunk_cell, G, rb0, rb1, cellsum)
         out = K.zeros((len(ks),), torch.float64)
         with self.span('sil_finish'):
             for j, (lab, k, cnt) in enumerate(zip(labels_list, ks, counts_list)):

@@ -193,6 +193,11 @@ class CudaKernels:
         nv.call('vtf_sil_sweep', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
                 c_i64(rb_begin), c_i64(rb_end), ptr(cellsum), stream())
 
+    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum):
+        P, d = Xh.shape
+        nv.call('vtf_sil_sweep_sym', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
+                c_int(rank), c_int(world), ptr(cellsum), stream())
+
     def sil_finish_cells(self, cellsum, cell_to_cluster, k, perm, labels, counts, p_begin, p_end, out_slot):
         n_cells, P = cellsum.shape
         nv.call('vtf_sil_finish_cells', ptr(cellsum), c_i64(P), c_int(n_cells), ptr(cell_to_cluster), c_int(k), ptr(perm),
