@@ -103,6 +103,25 @@ int vtf_lloyd_update(const double* sums, const int64_t* counts, const int64_t* n
                      int d, const float* C_old, float* C_new, double* C64, double* stats,
                      void* stream);
 
+/* Lock-step forms: ONE pass over X serves every k of the sweep (grouping.py:99-101 runs one fit per k; the fits
+ * are independent, so their iterations can share the reads).  Labelling L owns centre / cluster slots
+ * [k_off_h[L], k_off_h[L+1]) of the concatenated arrays (k_off_h is a HOST array of n_lab+1 ints, k_off_h[0] = 0)
+ * and the label vector labels[L * label_stride + row]; bit L of `active` clear = that fit has converged and is
+ * skipped.  At most 32 labellings and sum(k) <= 100 per call.  Semantics per labelling as the single forms.   */
+int vtf_lloyd_assign_multi(const float* Xc, int64_t N, int d, const float* C_all, int n_lab,
+                           const int32_t* k_off_h, uint32_t active, int32_t* labels, int64_t label_stride,
+                           int64_t* counts, int64_t* n_changed, void* stream);
+int vtf_cluster_sums_multi(const float* X, int64_t N, int d, const int32_t* labels, int64_t label_stride,
+                           int n_lab, const int32_t* k_off_h, uint32_t active, double* sums, void* ws,
+                           void* stream);
+int vtf_cluster_dispersion_multi(const float* X, int64_t N, int d, const int32_t* labels,
+                                 int64_t label_stride, int n_lab, const int32_t* k_off_h, uint32_t active,
+                                 const double* C64, double* sq, double* rt, void* ws, void* stream);
+/* stats[L * stats_stride + {0: shift^2, 1: n_changed, 2+c: counts}] for every active labelling.               */
+int vtf_lloyd_update_multi(const double* sums, const int64_t* counts, const int64_t* n_changed, int n_lab,
+                           const int32_t* k_off_h, uint32_t active, int d, const float* C_old, float* C_new,
+                           double* C64, double* stats, int stats_stride, void* stream);
+
 /* ---- a3: nearest-reference classification (grouping.py:51-56) -----------------------------
  * Xn, Rn are cosine-normalised.  dist[N,R] = clip(1 - Xn.Rn^T, 0, 2) (fp32, kept for the
  * '%.4f' log, grouping.py:63); label[i] = argmin (first index), or R when

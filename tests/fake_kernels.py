@@ -89,6 +89,51 @@ class FakeKernels:
         stats[2:] = counts.to(torch.float64)
         return C_new, C_new.to(torch.float64), stats
 
+    # ---- lock-step forms, restated through the single-labelling ones
+    def lloyd_assign_multi(self, Xs, C_all, k_off, active, labels_all, b, counts, n_changed):
+        n = Xs.shape[0]
+        for L in range(len(k_off) - 1):
+            if not (active >> L) & 1:
+                continue
+            lo, hi = int(k_off[L]), int(k_off[L + 1])
+            lab = labels_all[L, b:b + n].clone()
+            cnt = torch.zeros(hi - lo, dtype=torch.int64)
+            ch = torch.zeros(1, dtype=torch.int64)
+            self.lloyd_assign(Xs, C_all[lo:hi].contiguous(), lab, cnt, ch)
+            labels_all[L, b:b + n] = lab
+            counts[lo:hi] += cnt
+            n_changed[L] += ch[0]
+
+    def cluster_sums_multi(self, Xs, labels_all, b, k_off, active):
+        n = Xs.shape[0]
+        out = torch.zeros((int(k_off[-1]), Xs.shape[1]), dtype=torch.float64)
+        for L in range(len(k_off) - 1):
+            if (active >> L) & 1:
+                lo, hi = int(k_off[L]), int(k_off[L + 1])
+                out[lo:hi] = self.cluster_sums(Xs, labels_all[L, b:b + n], hi - lo)
+        return out
+
+    def cluster_dispersion_multi(self, Xs, labels_all, b, k_off, active, C64_all):
+        n = Xs.shape[0]
+        sq = torch.zeros(int(k_off[-1]), dtype=torch.float64)
+        rt = torch.zeros(int(k_off[-1]), dtype=torch.float64)
+        for L in range(len(k_off) - 1):
+            if (active >> L) & 1:
+                lo, hi = int(k_off[L]), int(k_off[L + 1])
+                sq[lo:hi], rt[lo:hi], _ = self.cluster_dispersion(Xs, labels_all[L, b:b + n], C64_all[lo:hi])
+        return sq, rt
+
+    def lloyd_update_multi(self, sums, counts, n_changed, k_off, active, C_old, stats_stride):
+        C_new = C_old.clone()
+        stats = torch.zeros((len(k_off) - 1, stats_stride), dtype=torch.float64)
+        for L in range(len(k_off) - 1):
+            if (active >> L) & 1:
+                lo, hi = int(k_off[L]), int(k_off[L + 1])
+                cn, _, st = self.lloyd_update(sums[lo:hi], counts[lo:hi], n_changed[L:L + 1], C_old[lo:hi])
+                C_new[lo:hi] = cn
+                stats[L, :2 + hi - lo] = st
+        return C_new, C_new.to(torch.float64), stats
+
     def cosine_classify(self, Xn, Rn, thr):
         dist = np.clip(1.0 - _np(Xn) @ _np(Rn).T, 0, 2).astype(np.float32)
         lab = dist.argmin(1).astype(np.int64)

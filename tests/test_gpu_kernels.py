@@ -150,6 +150,53 @@ def test_lloyd_assign_and_sums(K, N, d, k):
     assert np.array_equal(st[2:], np.bincount(got, minlength=k).astype(np.float64)) and st[1] == 0
 
 
+@pytest.mark.parametrize('N,d,ks', [(5000, 512, [2, 3, 4, 5, 6]), (2001, 768, [2, 5]), (1500, 1024, [3, 7, 8]), (300, 64, [2])])
+def test_lockstep_kernels_equal_single_labelling_kernels(K, N, d, ks):
+    """One pass for several labellings (assign / sums / dispersion / update) must reproduce the per-k kernels."""
+    X = blobs(N, d, kc=6, seed=13, normalize=(d == 512))
+    Xc = dev((X - X.mean(0)).astype(np.float32))
+    rng = np.random.default_rng(3)
+    Cs = [Xc[torch.from_numpy(rng.choice(N, k, replace=False)).cuda()].contiguous() for k in ks]
+    off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    nL, ktot = len(ks), int(off[-1])
+    C_all = torch.cat(Cs).contiguous()
+    labels_all = torch.full((nL, N), -1, dtype=torch.int32, device='cuda')
+    counts = torch.zeros(ktot, dtype=torch.int64, device='cuda')
+    changed = torch.zeros(nL, dtype=torch.int64, device='cuda')
+    active = (1 << nL) - 1
+    if nL > 1:
+        active &= ~2                                          # labelling 1 frozen: must stay untouched
+    K.lloyd_assign_multi(Xc, C_all, off, active, labels_all, 0, counts, changed)
+    sums = K.cluster_sums_multi(Xc, labels_all, 0, off, active)
+    for L, (k, C) in enumerate(zip(ks, Cs)):
+        lo, hi = int(off[L]), int(off[L + 1])
+        if not (active >> L) & 1:
+            assert (labels_all[L] == -1).all() and int(counts[lo:hi].sum()) == 0 and int(changed[L]) == 0
+            continue
+        lab = torch.full((N,), -1, dtype=torch.int32, device='cuda')
+        cnt = torch.zeros(k, dtype=torch.int64, device='cuda')
+        ch = torch.zeros(1, dtype=torch.int64, device='cuda')
+        K.lloyd_assign(Xc, C, lab, cnt, ch)
+        assert torch.equal(labels_all[L], lab) and torch.equal(counts[lo:hi], cnt) and int(changed[L]) == int(ch[0]) == N
+        assert torch.equal(sums[lo:hi], K.cluster_sums(Xc, lab, k))          # deterministic: bit-equal
+    full = (1 << nL) - 1
+    labels_all[labels_all < 0] = 0
+    C64 = C_all.double().contiguous()
+    sq, rt = K.cluster_dispersion_multi(Xc, labels_all, 0, off, full, C64)
+    for L, k in enumerate(ks):
+        lo, hi = int(off[L]), int(off[L + 1])
+        s1, r1, _ = K.cluster_dispersion(Xc, labels_all[L].contiguous(), C64[lo:hi].contiguous())
+        assert torch.allclose(sq[lo:hi], s1, rtol=1e-13) and torch.allclose(rt[lo:hi], r1, rtol=1e-13)
+    sums = K.cluster_sums_multi(Xc, labels_all, 0, off, full)
+    counts = torch.cat([torch.bincount(labels_all[L].long(), minlength=k) for L, k in enumerate(ks)])
+    changed = torch.arange(nL, device='cuda', dtype=torch.int64)
+    C_new, C64n, stats = K.lloyd_update_multi(sums, counts, changed, off, full, C_all, 2 + max(ks))
+    for L, k in enumerate(ks):
+        lo, hi = int(off[L]), int(off[L + 1])
+        cn, _, st = K.lloyd_update(sums[lo:hi].contiguous(), counts[lo:hi].contiguous(), changed[L:L + 1].contiguous(), Cs[L])
+        assert torch.equal(C_new[lo:hi], cn) and torch.allclose(stats[L, :2 + k], st, rtol=1e-12)
+
+
 @pytest.mark.parametrize('N,d,R,thr', [(2000, 512, 32, 0.55), (777, 768, 5, 0.9), (100, 1024, 40, -1.0), (64, 64, 1, 0.3)])
 def test_classify_kernel(K, N, d, R, thr):
     B = blobs(N + R, d, kc=8, seed=0)

@@ -157,6 +157,27 @@ def test_unaligned_dimension_and_odd_sizes(engine, N, d):
     assert np.array_equal(engine.classify(X[:100], X[200:205], 0.6)[1], RC.classify_core(X[:100], X[200:205], 5, 0.6)[1])
 
 
+def test_lockstep_sweep_equals_per_k_loops(engine):
+    """The lock-step Lloyd (all k share each pass) against one loop per k: identical labels, n_iter, centres."""
+    X = blobs(20000, 512, kc=8, noise=1.0, seed=0)
+    ks = [2, 3, 4, 5, 6, 9]
+    engine.lockstep = True
+    ctx, a = engine.kmeans_sweep(X, ks, 0)
+    engine.lockstep = False
+    _, b = engine.kmeans_sweep(X, ks, 0, ctx=ctx)
+    engine.lockstep = True
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.labels, rb.labels) and ra.n_iter == rb.n_iter and ra.strict == rb.strict
+        assert torch.equal(ra.centers, rb.centers) and abs(ra.inertia - rb.inertia) <= 1e-9 * rb.inertia
+        assert torch.equal(ra.counts, rb.counts)
+    sa = engine.ch_db_scores_multi(ctx, [r.labels for r in a], ks, [r.counts for r in a])
+    for r, (ch, db) in zip(a, sa):
+        rch, rdb = RC.cluster_scores(X[:0], None)[1:] if False else (None, None)
+    ref = [(RC.sklearn.metrics.calinski_harabasz_score(X, r.labels.cpu().numpy()),
+            RC.sklearn.metrics.davies_bouldin_score(X, r.labels.cpu().numpy())) for r in a]
+    np.testing.assert_allclose(np.asarray(sa), np.asarray(ref), rtol=1e-5)
+
+
 def test_four_rows_error_like_reference(tmp_path):
     X = blobs(4, 512, kc=2, noise=0.5, seed=0)
     paths = fake_faces(str(tmp_path), 4)

@@ -84,6 +84,15 @@ def main():
     add('lloyd_assign k=%d' % k, lambda: K.lloyd_assign(X, C, labels, counts, nch), B + N * 8, 2.0 * N * k * d)
     add('cluster_sums k=%d' % k, lambda: K.cluster_sums(X, labels, k), B + N * 4)
     add('cluster_dispersion k=%d' % k, lambda: K.cluster_dispersion(X, labels, C64), B + N * 4)
+    ks = [2, 3, 4, 5, 6]
+    off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    C_all = X[torch.randint(0, N, (int(off[-1]),), device='cuda')].contiguous()
+    labels_all = torch.stack([torch.randint(0, kk, (N,), device='cuda', dtype=torch.int32) for kk in ks]).contiguous()
+    cnt_all = torch.zeros(int(off[-1]), dtype=torch.int64, device='cuda')
+    ch_all = torch.zeros(len(ks), dtype=torch.int64, device='cuda')
+    add('lloyd_assign_multi k=2..6', lambda: K.lloyd_assign_multi(X, C_all, off, 31, labels_all, 0, cnt_all, ch_all), B + 5 * N * 8, 2.0 * N * 20 * d)
+    add('cluster_sums_multi k=2..6', lambda: K.cluster_sums_multi(X, labels_all, 0, off, 31), B + 5 * N * 4)
+    add('cluster_dispersion_multi k=2..6', lambda: K.cluster_dispersion_multi(X, labels_all, 0, off, 31, C_all.double()), B + 5 * N * 4)
     add('cosine_classify R=32', lambda: K.cosine_classify(X, R, 0.9), B + N * 32 * 4 + N * 8, 2.0 * N * 32 * d)
     nd = min(N, 50_000)
     Xd = X[:nd].contiguous()

@@ -43,6 +43,17 @@ inline int fail(int code, const char* what, const char* detail) {
 
 int num_sms();
 
+// Several labellings of the same rows handled in one pass (the k-range of cluster_faces, grouping.py:99-108):
+// labelling L owns the centre / cluster slots [off[L], off[L+1]) of a concatenated [Ktot, d] array and the label
+// vector labels[L * label_stride + row].  Bit L of `active` clear = labelling frozen (converged): skipped.
+constexpr int kMaxSeg = 32;
+struct Segs {
+    int n;
+    int off[kMaxSeg + 1];
+    unsigned int active;
+    long long label_stride;
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

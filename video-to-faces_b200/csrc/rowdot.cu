@@ -12,9 +12,10 @@ constexpr int kRowsPerWarp = 2;
 constexpr int kMaxDV = 8;   // register-cached rows up to d = 1024
 
 struct LloydEpi {
-    int32_t* labels;
-    unsigned long long* counts;
-    unsigned long long* n_changed;
+    int32_t* labels;                 // [n_seg][label_stride]
+    unsigned long long* counts;      // [Ktot]
+    unsigned long long* n_changed;   // [n_seg]
+    Segs sg;
 };
 struct ClassifyEpi {
     float* dist;
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
     extern __shared__ __align__(16) float smem[];
     float* sC = smem;                          // [k*d] when C_SMEM
     float* sC2 = smem + (C_SMEM ? (size_t)k * d : 0);   // [k] squared norms (Lloyd)
-    __shared__ unsigned int s_changed;
+    __shared__ unsigned int s_changed[kMaxSeg];
     unsigned int* s_counts = reinterpret_cast<unsigned int*>(sC2 + k);   // [k]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
         float4* Cs = reinterpret_cast<float4*>(sC);
         for (int i = threadIdx.x; i < k * nvec; i += blockDim.x) Cs[i] = __ldg(Cg + i);
     }
-    if (threadIdx.x == 0) s_changed = 0;
+    if (threadIdx.x < kMaxSeg) s_changed[threadIdx.x] = 0;
     for (int c = threadIdx.x; c < k; c += blockDim.x) s_counts[c] = 0;
     __syncthreads();
     if (MODE == 0) {
@@ -62,7 +63,6 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
         __syncthreads();
     }
 
-    unsigned int my_changed = 0;
     const int64_t warps_total = (int64_t)gridDim.x * nwarps;
     const int64_t step = warps_total * kRowsPerWarp;
     int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * kRowsPerWarp;
@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
 #pragma unroll
             for (int v = 0; v < DV; ++v) { n0[v] = ldg_stream(a0 + lane + 32 * v); n1[v] = ldg_stream(a1 + lane + 32 * v); }
         }
-        if (MODE == 0 && lane == 0) {
-            old0 = le.labels[r0];
-            old1 = (r0 + 1 < N) ? le.labels[r0 + 1] : -1;
+        if (MODE == 0 && lane < le.sg.n) {      // lane L keeps the previous label of labelling L
+            old0 = le.labels[lane * le.sg.label_stride + r0];
+            old1 = (r0 + 1 < N) ? le.labels[lane * le.sg.label_stride + r0 + 1] : -1;
         }
     };
     prefetch(row0);
@@ -99,7 +99,13 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
         float best0 = INFINITY, best1 = INFINITY;
         int arg0 = 0, arg1 = 0;
         float keep0 = 0.f, keep1 = 0.f;   // classify: lane (c & 31) keeps distance c for the coalesced store
+        int seg = 0;                      // Lloyd: current labelling
         for (int c = 0; c < k; ++c) {
+            if (MODE == 0 && c == le.sg.off[seg] && !((le.sg.active >> seg) & 1u)) {
+                c = le.sg.off[seg + 1] - 1;   // frozen labelling: skip its centres
+                ++seg;
+                continue;
+            }
             const float4* cr = reinterpret_cast<const float4*>(C_SMEM ? sC + (size_t)c * d : C + (size_t)c * d);
             float p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;   // two partial sums per row: shorter FMA chains
             if (DV > 0) {
@@ -133,17 +139,27 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
             }
             if (s0 < best0) { best0 = s0; arg0 = c; }   // strict '<': first index wins
             if (s1 < best1) { best1 = s1; arg1 = c; }
+            if (MODE == 0 && c == le.sg.off[seg + 1] - 1) {
+                // last centre of labelling `seg`: publish its labels, count changes, restart the argmin
+                const int p0 = __shfl_sync(0xffffffffu, prev0, seg), p1 = __shfl_sync(0xffffffffu, prev1, seg);
+                if (lane == 0) {
+                    const int base = le.sg.off[seg];
+                    unsigned int ch = (p0 != arg0 - base) ? 1u : 0u;
+                    le.labels[seg * le.sg.label_stride + row0] = arg0 - base;
+                    atomicAdd(&s_counts[arg0], 1u);
+                    if (has1) {
+                        ch += (p1 != arg1 - base) ? 1u : 0u;
+                        le.labels[seg * le.sg.label_stride + row0 + 1] = arg1 - base;
+                        atomicAdd(&s_counts[arg1], 1u);
+                    }
+                    if (ch) atomicAdd(&s_changed[seg], ch);
+                }
+                best0 = best1 = INFINITY;
+                ++seg;
+            }
         }
         if (lane == 0) {
             if (MODE == 0) {
-                if (prev0 != arg0) ++my_changed;
-                le.labels[row0] = arg0;
-                atomicAdd(&s_counts[arg0], 1u);
-                if (has1) {
-                    if (prev1 != arg1) ++my_changed;
-                    le.labels[row0 + 1] = arg1;
-                    atomicAdd(&s_counts[arg1], 1u);
-                }
             } else {
                 const bool on = ce.thr >= 0.f;   // false for NaN as well
                 ce.label[row0] = (on && best0 >= ce.thr) ? (int64_t)k : (int64_t)arg0;
@@ -152,11 +168,11 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ X
         }
     }
     if (MODE == 0) {
-        if (lane == 0 && my_changed) atomicAdd(&s_changed, my_changed);
         __syncthreads();
         for (int c = threadIdx.x; c < k; c += blockDim.x)
             if (s_counts[c]) atomicAdd(le.counts + c, (unsigned long long)s_counts[c]);
-        if (threadIdx.x == 0 && s_changed) atomicAdd(le.n_changed, (unsigned long long)s_changed);
+        if (threadIdx.x < le.sg.n && s_changed[threadIdx.x])
+            atomicAdd(le.n_changed + threadIdx.x, (unsigned long long)s_changed[threadIdx.x]);
     }
 }
 
@@ -202,16 +218,32 @@ int vtf_lloyd_assign(const float* Xc, int64_t N, int d, const float* C, int k, i
     VTF_REQUIRE(Xc && C && labels && counts && n_changed && N >= 0 && d > 0 && d % 4 == 0 && k > 0,
                 "vtf_lloyd_assign");
     if (N == 0) return VTF_OK;
-    LloydEpi le{labels, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(n_changed)};
+    LloydEpi le{labels, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(n_changed), {}};
+    le.sg.n = 1; le.sg.off[0] = 0; le.sg.off[1] = k; le.sg.active = 1u; le.sg.label_stride = 0;
     ClassifyEpi ce{nullptr, nullptr, -1.f};
     return launch_rowdot<0>(Xc, N, d, C, k, le, ce, stream, "vtf_lloyd_assign");
+}
+
+int vtf_lloyd_assign_multi(const float* Xc, int64_t N, int d, const float* C_all, int n_lab, const int32_t* k_off_h,
+                           uint32_t active, int32_t* labels, int64_t label_stride, int64_t* counts, int64_t* n_changed,
+                           void* stream) {
+    VTF_REQUIRE(Xc && C_all && k_off_h && labels && counts && n_changed && N >= 0 && d > 0 && d % 4 == 0 && n_lab > 0 &&
+                    n_lab <= kMaxSeg && label_stride >= N,
+                "vtf_lloyd_assign_multi (at most 32 labellings per call)");
+    if (N == 0 || active == 0) return VTF_OK;
+    LloydEpi le{labels, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(n_changed), {}};
+    le.sg.n = n_lab; le.sg.active = active; le.sg.label_stride = label_stride;
+    for (int i = 0; i <= n_lab; ++i) le.sg.off[i] = k_off_h[i];
+    VTF_REQUIRE(k_off_h[0] == 0 && k_off_h[n_lab] > 0, "vtf_lloyd_assign_multi: k_off must start at 0");
+    ClassifyEpi ce{nullptr, nullptr, -1.f};
+    return launch_rowdot<0>(Xc, N, d, C_all, k_off_h[n_lab], le, ce, stream, "vtf_lloyd_assign_multi");
 }
 
 int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int R, float thr, float* dist,
                         int64_t* label, void* stream) {
     VTF_REQUIRE(Xn && Rn && dist && label && N >= 0 && d > 0 && d % 4 == 0 && R > 0, "vtf_cosine_classify");
     if (N == 0) return VTF_OK;
-    LloydEpi le{nullptr, nullptr, nullptr};
+    LloydEpi le{nullptr, nullptr, nullptr, {}};
     ClassifyEpi ce{dist, label, thr};
     return launch_rowdot<1>(Xn, N, d, Rn, R, le, ce, stream, "vtf_cosine_classify");
 }

@@ -30,6 +30,10 @@ SIGNATURES = {
     'vtf_cluster_sums': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'vtf_cluster_dispersion': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_lloyd_update': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_lloyd_assign_multi': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, ctypes.c_uint32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    'vtf_cluster_sums_multi': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    'vtf_cluster_dispersion_multi': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_lloyd_update_multi': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),

@@ -78,6 +78,7 @@ class GroupingEngine:
         self.device = kernels.device
         self.profile = False
         self.events = []
+        self.lockstep = True     # all fits of a k-range share each pass over X (False: one Lloyd loop per k)
         self.sym = None          # None: symmetric silhouette sweep for large inputs; True / False forces it
 
     def span(self, name, flops=0.0):
@@ -313,6 +314,101 @@ class GroupingEngine:
         return KMeansResult(k=k, labels=labels, centers=centers, inertia=inertia, n_iter=n_iter,
                             counts=counts, strict=strict)
 
+    @staticmethod
+    def _pack_groups(ks, d):
+        """Labellings that share one pass: at most 32 per call, sum(k) <= 96 and all centres within ~160 KB of
+        shared memory (k = 2..6 at d = 512 is one group; k = 2..32 at d = 1024 becomes several)."""
+        groups, cur, tot = [], [], 0
+        for j, k in enumerate(ks):
+            if cur and (len(cur) >= 32 or tot + k > 96 or (tot + k) * d * 4 > 160 * 1024):
+                groups.append(cur)
+                cur, tot = [], 0
+            cur.append(j)
+            tot += k
+        if cur:
+            groups.append(cur)
+        return groups
+
+    def lloyd_multi(self, ctx, C0_list, max_iter=300):
+        """Every fit of the k-range in lock step: one read of X per iteration serves all k that are still iterating
+        (each fit keeps its own stopping rule and freezes when it is done, so results equal the separate fits)."""
+        out = [None] * len(C0_list)
+        ks = [int(c.shape[0]) for c in C0_list]
+        for grp in self._pack_groups(ks, ctx.d):
+            for j, r in zip(grp, self._lloyd_group(ctx, [C0_list[j] for j in grp], max_iter)):
+                out[j] = r
+        return out
+
+    def _lloyd_group(self, ctx, C0s, max_iter):
+        K, comm = self.K, self.comm
+        N, d, b, e = ctx.N, ctx.d, ctx.b, ctx.e
+        nL = len(C0s)
+        ks = [int(c.shape[0]) for c in C0s]
+        off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+        ktot = int(off[-1])
+        stride = 2 + max(ks)
+        C_all = torch.cat([c.contiguous() for c in C0s]).contiguous()
+        labels_all = torch.full((nL, N), -1, dtype=torch.int32, device=self.device)
+        Xs = ctx.Xc[b:e]
+        active = (1 << nL) - 1
+        n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
+        red = K.zeros((ktot * d + ktot + nL,), torch.float64)
+        for it in range(max_iter):
+            counts = K.zeros((ktot,), torch.int64)
+            changed = K.zeros((nL,), torch.int64)
+            K.lloyd_assign_multi(Xs, C_all, off, active, labels_all, b, counts, changed)
+            sums = K.cluster_sums_multi(Xs, labels_all, b, off, active)
+            if comm.active:
+                red[:ktot * d] = sums.view(-1)
+                red[ktot * d:ktot * d + ktot] = counts.to(torch.float64)
+                red[ktot * d + ktot:] = changed.to(torch.float64)
+                comm.allreduce_sum(red)
+                sums = red[:ktot * d].view(ktot, d).clone()
+                counts = red[ktot * d:ktot * d + ktot].round().to(torch.int64)
+                changed = red[ktot * d + ktot:].round().to(torch.int64)
+            C_new, _, stats = K.lloyd_update_multi(sums, counts, changed, off, active, C_all, stride)
+            st = stats.cpu().numpy()                                           # the one D2H of the iteration
+            for L in range(nL):
+                if not (active >> L) & 1:
+                    continue
+                lo, hi = int(off[L]), int(off[L + 1])
+                stL = st[L, :2 + hi - lo]
+                if (stL[2:] == 0).any():                                       # empty cluster: relocate (rare)
+                    cn, _, stL = self._relocate_empty(ctx, labels_all[L], C_all[lo:hi].contiguous(), sums[lo:hi].contiguous(),
+                                                      counts[lo:hi].contiguous(), changed[L:L + 1].contiguous(), stL)
+                    C_new[lo:hi] = cn
+                n_iter[L] = it + 1
+                if stL[1] == 0:                                                # labels == labels_old, _kmeans.py:723
+                    strict[L] = True
+                    active &= ~(1 << L)
+                    counts_fin[L] = counts[lo:hi].clone()
+                elif stL[0] <= ctx.tol:                                        # _kmeans.py:731-738
+                    active &= ~(1 << L)
+            C_all = C_new                                                      # _kmeans.py:721
+            if active == 0:
+                break
+        redo = sum(1 << L for L in range(nL) if not strict[L])
+        if redo:                                                               # _kmeans.py:742-754
+            counts = K.zeros((ktot,), torch.int64)
+            changed = K.zeros((nL,), torch.int64)
+            K.lloyd_assign_multi(Xs, C_all, off, redo, labels_all, b, counts, changed)
+            comm.allreduce_sum(counts)
+            for L in range(nL):
+                if not strict[L]:
+                    counts_fin[L] = counts[int(off[L]):int(off[L + 1])].clone()
+        sq, _ = K.cluster_dispersion_multi(Xs, labels_all, b, off, (1 << nL) - 1, C_all.to(torch.float64))
+        comm.allreduce_sum(sq)
+        sq_h = sq.cpu().numpy()
+        res = []
+        for L in range(nL):
+            lo, hi = int(off[L]), int(off[L + 1])
+            lab = labels_all[L]
+            comm.allgather_rows(lab, ctx.bounds)
+            centers = (C_all[lo:hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()  # _kmeans.py:1543-1546
+            res.append(KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
+                                    n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L]))
+        return res
+
     def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):
         """SK/cluster/_k_means_common.pyx:167-211: give every empty cluster the point farthest from
         its own (old) centre.  Rare; O(k) host steps around one extra pass over X."""
@@ -354,54 +450,73 @@ class GroupingEngine:
             for trials, ks in by_trials.items():
                 with self.span('kmeans++'):
                     seed_cache[trials] = self.kmeans_plusplus(ctx, max(ks), rstate)
+        C0s, seeds_all = [], []
         for j, k in enumerate(clusters):
             if inits is None:
                 seeds = seed_cache[n_local_trials(k)][:k]
                 C0 = self.K.gather_rows(ctx.Xc, torch.from_numpy(seeds).to(self.device))
             else:
                 seeds = None
-                C0 = (self._pad16(self.to_device(inits[j])) - ctx.mean32).contiguous()
-            with self.span('lloyd'):
-                res = self.lloyd(ctx, C0)
-            res.seeds = seeds
-            results.append(res)
+                C0 = (self._pad16(self.to_device(inits[j]), ctx.d) - ctx.mean32).contiguous()
+            C0s.append(C0)
+            seeds_all.append(seeds)
+        with self.span('lloyd'):
+            results = self.lloyd_multi(ctx, C0s) if self.lockstep else [self.lloyd(ctx, c) for c in C0s]
+        for r, sd in zip(results, seeds_all):
+            r.seeds = sd
         return ctx, results
 
     # ------------------------------------------------------------------------------ a9 / a10
     def ch_db_scores(self, ctx, labels, k, counts=None):
-        """calinski_harabasz_score and davies_bouldin_score (SK/metrics/cluster/_unsupervised.py:333-487):
-        one pass for the per-cluster sums, one for the distances to the cluster means."""
+        """calinski_harabasz_score and davies_bouldin_score for one labelling (see ch_db_scores_multi)."""
+        return self.ch_db_scores_multi(ctx, [labels], [k], [counts])[0]
+
+    def ch_db_scores_multi(self, ctx, labels_list, ks, counts_list=None):
+        """calinski_harabasz_score and davies_bouldin_score (SK/metrics/cluster/_unsupervised.py:333-487) for every
+        labelling of the k-range with TWO passes over X in total: one for all per-cluster sums, one for all
+        distances to the cluster means (the reference makes both passes once per k)."""
         K, comm = self.K, self.comm
         b, e = ctx.b, ctx.e
-        if counts is None:
-            counts = torch.bincount(labels.to(torch.int64), minlength=k)
-        sums = K.cluster_sums(ctx.X[b:e], labels[b:e], k)
-        comm.allreduce_sum(sums)
-        cnt = counts.to(torch.float64)
-        means = sums / cnt.clamp_min(1).unsqueeze(1)
-        sq, rt, _ = K.cluster_dispersion(ctx.X[b:e], labels[b:e], means.contiguous())
-        both = torch.cat([sq, rt])
-        comm.allreduce_sum(both)
-        sq, rt = both[:k], both[k:]
-        present = counts > 0
-        n_labels = int(present.sum().item())
-        self._check_n_labels(n_labels, ctx.N)
-        means, cnt, sq, rt = means[present], cnt[present], sq[present], rt[present]
-        # CH (:394-403)
-        extra = float((cnt * ((means - ctx.mean64) ** 2).sum(1)).sum().item())
-        intra = float(sq.sum().item())
-        ch = 1.0 if intra == 0.0 else extra * (ctx.N - n_labels) / (intra * (n_labels - 1.0))
-        # DB (:467-487)
-        intra_d = (rt / cnt).cpu().numpy()
-        m = means.cpu().numpy()
-        cd = np.sqrt(np.maximum(((m[:, None, :] - m[None, :, :]) ** 2).sum(-1), 0.0))
-        if np.allclose(intra_d, 0) or np.allclose(cd, 0):
-            db = 0.0
-        else:
-            cd[cd == 0] = np.inf
-            comb = intra_d[:, None] + intra_d
-            db = float(np.mean(np.max(comb / cd, axis=1)))
-        return float(ch), float(db)
+        if counts_list is None:
+            counts_list = [None] * len(ks)
+        counts_list = [c if c is not None else torch.bincount(l.to(torch.int64), minlength=k)
+                       for c, l, k in zip(counts_list, labels_list, ks)]
+        out = [None] * len(ks)
+        for grp in self._pack_groups(ks, 0):
+            gk = [ks[j] for j in grp]
+            off = np.concatenate([[0], np.cumsum(gk)]).astype(np.int32)
+            nL = len(grp)
+            labels_all = torch.stack([labels_list[j] for j in grp]).contiguous()
+            full = (1 << nL) - 1
+            sums = K.cluster_sums_multi(ctx.X[b:e], labels_all, b, off, full)
+            comm.allreduce_sum(sums)
+            cnt_all = torch.cat([counts_list[j] for j in grp]).to(torch.float64)
+            means = (sums / cnt_all.clamp_min(1).unsqueeze(1)).contiguous()
+            sq, rt = K.cluster_dispersion_multi(ctx.X[b:e], labels_all, b, off, full, means)
+            both = torch.cat([sq, rt])
+            comm.allreduce_sum(both)
+            ktot = int(off[-1])
+            sq_h, rt_h = both[:ktot].cpu().numpy(), both[ktot:].cpu().numpy()
+            means_h, cnt_h, mean_h = means.cpu().numpy(), cnt_all.cpu().numpy(), ctx.mean64.cpu().numpy()
+            for L, j in enumerate(grp):
+                lo, hi = int(off[L]), int(off[L + 1])
+                present = cnt_h[lo:hi] > 0
+                n_labels = int(present.sum())
+                self._check_n_labels(n_labels, ctx.N)
+                m, cnt, sqL, rtL = means_h[lo:hi][present], cnt_h[lo:hi][present], sq_h[lo:hi][present], rt_h[lo:hi][present]
+                extra = float((cnt * ((m - mean_h) ** 2).sum(1)).sum())          # CH (:394-403)
+                intra = float(sqL.sum())
+                ch = 1.0 if intra == 0.0 else extra * (ctx.N - n_labels) / (intra * (n_labels - 1.0))
+                intra_d = rtL / cnt                                               # DB (:467-487)
+                cd = np.sqrt(np.maximum(((m[:, None, :] - m[None, :, :]) ** 2).sum(-1), 0.0))
+                if np.allclose(intra_d, 0) or np.allclose(cd, 0):
+                    db = 0.0
+                else:
+                    cd[cd == 0] = np.inf
+                    comb = intra_d[:, None] + intra_d
+                    db = float(np.mean(np.max(comb / cd, axis=1)))
+                out[j] = (float(ch), float(db))
+        return out
 
     @staticmethod
     def _check_n_labels(n_labels, n_samples):
@@ -529,9 +644,6 @@ class GroupingEngine:
         labels = [r.labels for r in results]
         counts = [r.counts for r in results]
         sil = self.silhouette_scores(ctx, labels, ks, counts, force=force)
-        out = []
         with self.span('ch_db'):
-            for r, s in zip(results, sil):
-                ch, db = self.ch_db_scores(ctx, r.labels, r.k, r.counts)
-                out.append((r.k, float(s), ch, db))
-        return out
+            chdb = self.ch_db_scores_multi(ctx, labels, ks, counts)
+        return [(r.k, float(s), ch, db) for r, s, (ch, db) in zip(results, sil, chdb)]

@@ -121,6 +121,52 @@ class CudaKernels:
                 ptr(C64), ptr(stats), stream())
         return C_new, C64, stats
 
+    # ---- lock-step forms: labels_all is int32 [n_lab, N_total]; the kernels see rows [b, e) of every labelling
+    @staticmethod
+    def _koff(k_off):
+        import ctypes
+        import numpy as np
+        a = np.ascontiguousarray(k_off, dtype=np.int32)
+        return a, a.ctypes.data_as(ctypes.c_void_p)
+
+    def lloyd_assign_multi(self, Xs, C_all, k_off, active, labels_all, b, counts, n_changed):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        lab_ptr = nv.c_vp(labels_all.data_ptr() + 4 * b)
+        nv.call('vtf_lloyd_assign_multi', ptr(Xs), c_i64(n), c_int(d), ptr(C_all), c_int(len(k_off) - 1), koff, active, lab_ptr,
+                c_i64(labels_all.shape[1]), ptr(counts), ptr(n_changed), stream())
+
+    def cluster_sums_multi(self, Xs, labels_all, b, k_off, active):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        ktot = int(k_off[-1])
+        sums = self.zeros((ktot, d), torch.float64)
+        ws = self._workspace(nv.load().vtf_cluster_sums_ws_bytes(ktot, d))
+        nv.call('vtf_cluster_sums_multi', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b),
+                c_i64(labels_all.shape[1]), c_int(len(k_off) - 1), koff, active, ptr(sums), ptr(ws), stream())
+        return sums
+
+    def cluster_dispersion_multi(self, Xs, labels_all, b, k_off, active, C64_all):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        ktot = int(k_off[-1])
+        sq = self.zeros((ktot,), torch.float64)
+        rt = self.zeros((ktot,), torch.float64)
+        ws = self._workspace(nv.load().vtf_cluster_sums_ws_bytes(ktot, d))
+        nv.call('vtf_cluster_dispersion_multi', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b),
+                c_i64(labels_all.shape[1]), c_int(len(k_off) - 1), koff, active, ptr(C64_all), ptr(sq), ptr(rt), ptr(ws), stream())
+        return sq, rt
+
+    def lloyd_update_multi(self, sums, counts, n_changed, k_off, active, C_old, stats_stride):
+        ktot, d = C_old.shape
+        keep, koff = self._koff(k_off)
+        C_new = C_old.clone()                          # frozen labellings keep their centres
+        C64 = C_old.to(torch.float64)
+        stats = self.zeros((len(k_off) - 1, stats_stride), torch.float64)
+        nv.call('vtf_lloyd_update_multi', ptr(sums), ptr(counts), ptr(n_changed), c_int(len(k_off) - 1), koff, active, c_int(d),
+                ptr(C_old), ptr(C_new), ptr(C64), ptr(stats), c_int(stats_stride), stream())
+        return C_new, C64, stats
+
     # ------------------------------------------------------------------ a3 / a1
     def cosine_classify(self, Xn, Rn, thr):
         N, d = self._chk(Xn)
