@@ -69,13 +69,26 @@ template <bool PAIR, bool SYM>
 __device__ __forceinline__ bool next_work(const Params& prm, int64_t it, int64_t unit0, int64_t unit_stride,
                                           int64_t& rbu, int& t0, int& t1) {
     if (SYM) {
+        // Unit pair (q, U-1-q) owns the virtual tile list [0, U+1): first the U-q tiles of unit q (t = q + i), then
+        // the q+1 tiles of unit U-1-q.  Every pair has the same length, and each is cut into prm.n_seg equal
+        // sub-ranges so that the work items are small against the number of CTA pairs (tail effect); a sub-range
+        // that straddles the two units yields two pieces (it & 1), each with its own A block.
         const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
-        const int64_t q = prm.sym_rank + (unit0 + (it >> 1) * unit_stride) * prm.sym_world;
+        const int64_t w = unit0 + (it >> 1) * unit_stride;             // sub-item of this rank
+        const int64_t q = prm.sym_rank + (w / prm.n_seg) * prm.sym_world;
         if (q >= n_q) return false;
-        const int64_t u = (it & 1) ? U - 1 - q : q;
-        rbu = u;
-        if ((it & 1) && u == q) { t0 = t1 = 0; return true; }      // middle unit of an odd U: already done
-        t0 = (int)u; t1 = (int)U;
+        const int64_t ub = U - 1 - q;
+        const int64_t len_a = U - q, len_tot = (ub == q) ? len_a : U + 1;
+        const int64_t L = (len_tot + prm.n_seg - 1) / prm.n_seg;
+        const int64_t lo = (w % prm.n_seg) * L, hi = min(lo + L, len_tot);
+        if (!(it & 1)) {                                               // piece of unit q
+            rbu = q;
+            t0 = (int)(q + min(lo, len_a)); t1 = (int)(q + min(hi, len_a));
+        } else {                                                       // piece of unit U-1-q
+            rbu = ub;
+            t0 = (int)(ub + max(lo, len_a) - len_a); t1 = (int)(ub + max(hi, len_a) - len_a);
+        }
+        if (t1 < t0) t1 = t0;
         return true;
     }
     const int64_t n_items = (prm.n_rb / (PAIR ? 2 : 1)) * prm.n_seg;
@@ -471,13 +484,19 @@ extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int
     prm.rb_begin = 0; prm.n_rb = P / tc::BM;
     prm.n_kb = d / tc::BK;
     prm.n_tiles = (int)(P / tc::BN);
-    prm.n_seg = 1; prm.tiles_per_seg = prm.n_tiles;
+    prm.tiles_per_seg = prm.n_tiles;
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = rank; prm.sym_world = world;
     const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
     if (rank >= n_q) return VTF_OK;
     const int64_t mine = (n_q - rank + world - 1) / world;
-    const int grid = 2 * (int)min((int64_t)(num_sms() / 2), mine);
+    // cut every unit pair into sub-ranges until there are >= 12 work items per CTA pair (tail effect <= ~8%),
+    // but keep at least 8 tiles per sub-range so the resident A block is amortised
+    const int64_t slots = num_sms() / 2;
+    int n_seg = 1;
+    while (mine * n_seg < 12 * slots && (U + 1) / (2 * n_seg) >= 8) n_seg *= 2;
+    prm.n_seg = n_seg;
+    const int grid = 2 * (int)min(slots, mine * n_seg);
     if (d <= 512) return tc::launch<true, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
     return tc::launch<false, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
 }

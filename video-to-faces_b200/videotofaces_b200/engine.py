@@ -241,23 +241,28 @@ class GroupingEngine:
         comm.allgather_rows(closest, ctx.bounds)
         comm.allreduce_sum(pots)
         pot = np.float32(pots.cpu().numpy()[0])                                # _kmeans.py:243
+        picks = []                                                             # (candidate ids on device, winner) per round
         for _ in range(1, k):
             rand_vals = rs.uniform(size=trials) * np.float64(pot)              # _kmeans.py:249
             thr = _ceil_to_f32(rand_vals)
             order = np.argsort(thr, kind='stable')
-            picked = K.kpp_pick(closest, torch.from_numpy(thr[order]).to(self.device)).cpu().numpy()
-            cand = np.empty(trials, dtype=np.int64)
-            cand[order] = picked
-            cand[cand < 0] = N - 1                                             # _kmeans.py:254 clip
-            cand_t = torch.from_numpy(cand).to(self.device)
+            inv = np.empty_like(order)
+            inv[order] = np.arange(trials)
+            picked = K.kpp_pick(closest, torch.from_numpy(thr[order]).to(self.device))
+            # back to draw order, never-reached thresholds clip to N-1 (_kmeans.py:254): all on the device, no sync
+            cand_t = picked[torch.from_numpy(inv).to(self.device)]
+            cand_t = torch.where(cand_t < 0, torch.full_like(cand_t, N - 1), cand_t)
             out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand_t), closest[b:e])   # :257-263
             comm.allreduce_sum(pots)
-            pots32 = pots.cpu().numpy().astype(np.float32)
+            pots32 = pots.cpu().numpy().astype(np.float32)                     # the one D2H of the round
             best = int(np.argmin(pots32))                                      # _kmeans.py:266
             pot = pots32[best]
             closest[b:e] = out[best]
             comm.allgather_rows(closest, ctx.bounds)
-            seeds.append(int(cand[best]))
+            picks.append((cand_t, best))
+        if picks:
+            chosen = torch.stack([c[bst] for c, bst in picks]).cpu().numpy()
+            seeds.extend(int(v) for v in chosen)
         return np.asarray(seeds, dtype=np.int64)
 
     # ------------------------------------------------------------------------------ a6 Lloyd
