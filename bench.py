@@ -158,7 +158,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO'):
             os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line the driver reads
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import __graft_entry__ as ge
