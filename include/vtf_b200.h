@@ -67,6 +67,13 @@ int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T,
  * when thr[t] is not reached inside this shard.                                            */
 int vtf_kpp_pick(const float* closest, int64_t N, const float* thr, int T,
                  const float* offset_in, float* total_out, int64_t* idx, void* stream);
+/* Round glue on the device (no host round trip per k-means++ round).  round_prep: best = argmin of the fp32-rounded
+ * potentials of the previous round (:266, first minimum), pot = that potential; thr[t] = smallest fp32 >= u[t] * pot
+ * (:249; u = the round's uniform draws, made in advance on the host by numpy's MT19937 -- they do not depend on the
+ * data), sorted ascending, order[t] = draw index of thr[t].  unsort: cand[order[t]] = picked[t], -1 -> N-1 (:254).  */
+int vtf_kpp_round_prep(const double* pots, int n_pots, const double* u, int T, float* thr, int32_t* order,
+                       int64_t* best, void* stream);
+int vtf_kpp_unsort(const int64_t* picked, const int32_t* order, int T, int64_t N, int64_t* cand, void* stream);
 /* The same result from the plain one-thread chain (N dependent fp32 adds).  vtf_kpp_pick reproduces that chain
  * bit for bit with block-wide integer prefix sums inside each binade of the running sum and falls back to single
  * steps only at ties, binade changes and oversized addends; this entry point is the cross-check.  */
@@ -210,6 +217,13 @@ int vtf_sil_finish_cells(const float* cellsum, int64_t P, int n_cells,
                          const int32_t* cell_to_cluster, int k, const int64_t* perm,
                          const int32_t* labels, const int64_t* counts,
                          int64_t p_begin, int64_t p_end, double* out_sum, void* stream);
+
+/* ---- f3: test_grouping (grouping.py:140-155) -- rand_score's contingency table ------------------
+ * table[a[i]*nb + b[i]] += 1 over the rows given (sklearn.metrics.cluster.contingency_matrix, the input of
+ * pair_confusion_matrix / rand_score, SK/metrics/cluster/_supervised.py:106-192, 195-271, 280-357); a in [0,na), b in [0,nb),
+ * anything else is counted in *bad.  Shards add across ranks.                                          */
+int vtf_contingency(const int32_t* a, const int32_t* b, int64_t N, int na, int nb, int64_t* table, int64_t* bad,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ import numpy as np
 
 ROOT = osp.dirname(osp.dirname(osp.abspath(__file__)))
 sys.path.insert(0, osp.join(ROOT, 'video-to-faces_b200'))
-from videotofaces_b200.synth import blobs, plant_dupes  # noqa: E402
+from videotofaces_b200.synth import blobs, blob_truth, plant_dupes  # noqa: E402
 sys.path.insert(0, ROOT)
 from oracle.make_hashes import make_hashes  # noqa: E402
 
@@ -136,7 +136,55 @@ def golden_cluster(name, X, clusters, rstate):
     return dict(stdout_all=out, stdout_best=out2)
 
 
+def golden_testmode(name, X, R, gt, thr, rstate, exclude_other):
+    """test_grouping (grouping.py:140-155) of the real reference.  Its encoder calls are the one part that cannot run
+    here (no weights offline) and are not on the path: they are replaced by look-ups into X / R; classify, KMeans,
+    rand_score, silhouette_score and the printed line are the reference's own."""
+    saved = ref_grouping.get_encoder_model, ref_grouping.encode_faces, ref_grouping.encode_refs
+    ref_grouping.get_encoder_model = lambda style, mname, device: None
+    ref_grouping.encode_faces = lambda paths, model, bs, area: np.ascontiguousarray(
+        X[[int(osp.basename(p)[1:7]) for p in paths]])
+    ref_grouping.encode_refs = lambda refs, model: R
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            paths = fake_faces(td, X.shape[0])
+            with open(osp.join(td, 'labels.txt'), 'w') as f:
+                f.write('\n'.join(str(int(g)) for g in gt) + '\n')
+            refs = [('c%02d' % i, ['unused.jpg']) for i in range(R.shape[0])]
+            params = ('live', 'facenet_vgg', 'cpu', td, exclude_other, 16, None, thr, rstate)
+            _, out = quiet(ref_grouping.test_grouping, paths, refs, params)
+            with open(osp.join(td, 'faces', 'log_classification.csv')) as f:
+                log = f.read()
+    finally:
+        ref_grouping.get_encoder_model, ref_grouping.encode_faces, ref_grouping.encode_refs = saved
+    with open(osp.join(GOLD, name + '.log_classification.csv'), 'w') as f:
+        f.write(log)
+    return dict(stdout=out)
+
+
+def testmode_cases(man):
+    # noise 5: the blobs overlap enough that classification, clustering and the 'other' threshold all make mistakes
+    C, ids = blob_truth(500, 512, kc=5, seed=4)
+    X = blobs(500, 512, kc=5, noise=5.0, seed=4)
+    R = (C + np.float32(0.15) * np.random.default_rng(9).standard_normal(C.shape, dtype=np.float32)).astype(np.float32)
+    gen = ("X=blobs(500,512,kc=5,noise=5,seed=4); C,ids=blob_truth(500,512,kc=5,seed=4); labels.txt=ids+1; "
+           "R=C+0.15*default_rng(9).standard_normal(C.shape,float32); ")
+    man['cases']['testmode_500x512'] = dict(gen=gen + "thr=0.97; rstate=0; exclude_other=False",
+                                            **golden_testmode('testmode_500x512', X, R, ids + 1, 0.97, 0, False))
+    man['cases']['testmode_500x512_excl'] = dict(gen=gen + "R=R[:4]; thr=0.97; rstate=0; exclude_other=True",
+                                                 **golden_testmode('testmode_500x512_excl', X, np.ascontiguousarray(R[:4]),
+                                                                   ids + 1, 0.97, 0, True))
+
+
 def main():
+    if '--testmode-only' in sys.argv:          # add the test_grouping cases to an existing manifest
+        with open(osp.join(GOLD, 'MANIFEST.json')) as f:
+            man = json.load(f)
+        testmode_cases(man)
+        with open(osp.join(GOLD, 'MANIFEST.json'), 'w') as f:
+            json.dump(man, f, indent=1, sort_keys=True)
+        print(json.dumps({k: v for k, v in man['cases'].items() if k.startswith('testmode')}, indent=1))
+        return
     import sklearn, scipy
     os.makedirs(GOLD, exist_ok=True)
     man = dict(sklearn=sklearn.__version__, numpy=np.__version__, scipy=scipy.__version__,
@@ -181,6 +229,8 @@ def main():
         man['cases']['cluster_4rows_error'] = 'no error?!'
     except ValueError as e:
         man['cases']['cluster_4rows_error'] = str(e)
+
+    testmode_cases(man)
 
     with open(osp.join(GOLD, 'MANIFEST.json'), 'w') as f:
         json.dump(man, f, indent=1, sort_keys=True)

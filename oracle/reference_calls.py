@@ -122,3 +122,13 @@ def kmeanspp_indices(X, k, rstate):
     Xc = X - X.mean(axis=0)
     _, idx = sklearn.cluster.kmeans_plusplus(Xc, k, random_state=rstate)
     return idx
+
+
+def testmode_scores(X, R, gt, n_clusters, thr, rstate):
+    """test_grouping, arithmetic only (grouping.py:146-151): (accuracy, rand score, silhouette score, labels)."""
+    _, inds = classify_core(X, R, R.shape[0], thr)                        # grouping.py:146
+    acc = np.count_nonzero(inds + 1 == gt) / gt.size                      # grouping.py:147
+    cm = sklearn.cluster.KMeans(n_clusters=n_clusters, random_state=rstate).fit(X)      # grouping.py:149
+    rand_scr = sklearn.metrics.rand_score(gt, cm.labels_)                 # grouping.py:150
+    silh_scr = sklearn.metrics.silhouette_score(X, cm.labels_)            # grouping.py:151
+    return acc, rand_scr, silh_scr, cm.labels_

@@ -310,3 +310,23 @@ def davies_bouldin_score(X, labels):
 def select_best(scores):
     """grouping.py:116 -- first maximum of the silhouette column."""
     return max(scores, key=lambda x: x[1])[0]
+
+
+def rand_score(labels_true, labels_pred):
+    """sklearn.metrics.rand_score (SK/metrics/cluster/_supervised.py:280-357) restated: contingency table (:106-192),
+    pair confusion matrix (:195-271), (n_00 + n_11) / all pairs; 1.0 in the two degenerate cases."""
+    a = np.unique(np.asarray(labels_true), return_inverse=True)[1]
+    b = np.unique(np.asarray(labels_pred), return_inverse=True)[1]
+    n = np.int64(a.shape[0])
+    na, nb = int(a.max()) + 1 if n else 0, int(b.max()) + 1 if n else 0
+    T = np.bincount(a.astype(np.int64) * nb + b, minlength=na * nb).reshape(na, nb).astype(np.int64)
+    n_c, n_k = T.sum(axis=1), T.sum(axis=0)
+    sum_squares = (T ** 2).sum()
+    c11 = sum_squares - n
+    c01 = T.dot(n_k).sum() - sum_squares
+    c10 = T.T.dot(n_c).sum() - sum_squares
+    c00 = n ** 2 - c01 - c10 - sum_squares
+    num, den = c00 + c11, c00 + c01 + c10 + c11
+    if num == den or den == 0:
+        return 1.0
+    return float(num / den)

@@ -56,6 +56,28 @@ class FakeKernels:
         idx[idx >= cs.size] = -1
         return torch.from_numpy(idx)
 
+    def kpp_round_prep(self, pots, u):
+        p32 = _np(pots).astype(np.float32)
+        best = int(np.argmin(p32))
+        v = _np(u) * np.float64(p32[best])
+        t = v.astype(np.float32)
+        low = t.astype(np.float64) < v
+        t[low] = np.nextafter(t[low], np.float32(np.inf))
+        order = np.argsort(t, kind='stable')
+        return (torch.from_numpy(t[order]), torch.from_numpy(order.astype(np.int32)),
+                torch.tensor([best], dtype=torch.int64))
+
+    def kpp_unsort(self, picked, order, N):
+        cand = torch.empty_like(picked)
+        cand[order.to(torch.int64)] = torch.where(picked < 0, torch.full_like(picked, N - 1), picked)
+        return cand
+
+    def contingency(self, a, b, na, nb):
+        a64, b64 = a.to(torch.int64), b.to(torch.int64)
+        ok = (a64 >= 0) & (a64 < na) & (b64 >= 0) & (b64 < nb)
+        table = torch.bincount(a64[ok] * nb + b64[ok], minlength=na * nb).view(na, nb)
+        return table, torch.tensor([int((~ok).sum())], dtype=torch.int64)
+
     def lloyd_assign(self, Xc, C, labels, counts, n_changed):
         new = torch.from_numpy(R.lloyd_assign(_np(Xc), _np(C)))
         n_changed += int((new != labels).sum())

@@ -118,6 +118,35 @@ def test_kpp_pick_parallel_scan_is_bit_exact(K, name):
         assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), ('serial' if serial else 'scan', name)
 
 
+@pytest.mark.parametrize('T', [1, 2, 3, 8])
+def test_kpp_round_glue_equals_the_host_arithmetic(K, T):
+    """argmin of the fp32-rounded potentials, thresholds = smallest fp32 >= u * pot (stable ascending order), and the
+    unsort + clip that follows the pick -- the device glue must equal numpy on the same numbers (SK _kmeans.py:249-266)."""
+    rng = np.random.default_rng(T)
+    for rep in range(20):
+        pots = rng.random(T) * 1e5 + 1.0
+        if T > 1 and rep % 3 == 0:
+            pots[1] = pots[0] = pots.min() * 0.5                 # tie after fp32 rounding too: first minimum wins
+        u = rng.random(T)
+        if T > 2 and rep % 4 == 0:
+            u[2] = u[0]                                          # equal thresholds: stable order
+        p32 = pots.astype(np.float32)
+        best = int(np.argmin(p32))
+        v = u * np.float64(p32[best])
+        t = v.astype(np.float32)
+        low = t.astype(np.float64) < v
+        t[low] = np.nextafter(t[low], np.float32(np.inf))
+        order = np.argsort(t, kind='stable')
+        thr_d, order_d, best_d = K.kpp_round_prep(dev(pots), dev(u))
+        assert int(best_d.item()) == best
+        assert thr_d.cpu().numpy().tobytes() == t[order].tobytes()
+        assert np.array_equal(order_d.cpu().numpy(), order)
+        picked = rng.integers(-1, 1000, T).astype(np.int64)
+        want = np.empty(T, np.int64)
+        want[order] = np.where(picked < 0, 999, picked)
+        assert np.array_equal(K.kpp_unsort(dev(picked), order_d, 1000).cpu().numpy(), want)
+
+
 @pytest.mark.parametrize('N,d,k', [(5000, 512, 6), (3001, 768, 3), (1000, 1024, 32), (33, 64, 2), (2000, 20, 4), (600, 1024, 60)])
 def test_lloyd_assign_and_sums(K, N, d, k):
     X = blobs(N, d, kc=min(k, 8), seed=11, normalize=(d == 512))

@@ -10,7 +10,7 @@ import torch
 
 from oracle import reference_calls as RC
 from oracle import restatement as RS
-from videotofaces_b200.synth import blobs, plant_dupes
+from videotofaces_b200.synth import blobs, eval_case, plant_dupes
 from videotofaces_b200 import dupes as vdupes, grouping as vgrouping
 from videotofaces_b200.main import video_to_faces
 
@@ -261,3 +261,48 @@ def test_full_size_properties_200k(engine):
         if i == 0:
             continue
         assert abs(D[r_i, :i].min() - mins[i]) <= 1e-6                   # exact rows against the oracle
+
+
+@pytest.mark.parametrize('name,excl', [('testmode_500x512', False), ('testmode_500x512_excl', True)])
+def test_test_grouping_golden(tmp_path, golden_dir, capsys, name, excl):
+    """test_grouping (grouping.py:140-155) through video_to_faces(_test_enc=True): the printed accuracy / rand score /
+    silhouette line and the classification log equal the real reference's."""
+    import json
+    X, R, gt = eval_case(excl)
+    paths = fake_faces(str(tmp_path), X.shape[0])
+    with open(tmp_path / 'labels.txt', 'w') as f:
+        f.write('\n'.join(str(int(g)) for g in gt) + '\n')
+    ref_dir = tmp_path / 'ref'
+    for i in range(R.shape[0]):
+        os.makedirs(ref_dir / ('c%02d' % i))
+        with open(ref_dir / ('c%02d' % i) / 'a.jpg', 'wb') as f:
+            f.write(b'x')
+    video_to_faces(mode='grouping', style='live', out_dir=str(tmp_path), input_path=str(tmp_path), clusters='2-6',
+                   ref_dir=str(ref_dir), enc_oth_thr=0.97, random_state=0, _test_enc=True, _test_exclude_other=excl,
+                   features=X, ref_features=R)
+    out = capsys.readouterr().out
+    with open(osp.join(golden_dir, 'MANIFEST.json')) as f:
+        want = json.load(f)['cases'][name]['stdout']
+    assert out.endswith(want), out
+    assert read(str(tmp_path / 'faces'), 'log_classification.csv') == read(golden_dir, name + '.log_classification.csv')
+
+
+@pytest.mark.parametrize('N,ka,kb', [(1_000_000, 6, 6), (300_001, 200, 150), (5, 3, 2), (70_000, 1, 7)])
+def test_rand_score_equals_sklearn(engine, N, ka, kb):
+    """Contingency histogram on the device (shared-memory and global-atomic forms) + exact integer pair counts."""
+    import sklearn.metrics
+    rng = np.random.default_rng(N)
+    a = rng.integers(0, ka, N) * 3 - 7                       # arbitrary integers, like labels.txt
+    b = rng.integers(0, kb, N).astype(np.int32)
+    b[: N // 3] = (a[: N // 3] // 3 + 2) % kb                # correlated part so the score is not just chance level
+    got = engine.rand_score(a, torch.from_numpy(b).cuda())
+    assert got == sklearn.metrics.rand_score(a, b)
+    assert got == RS.rand_score(a, b)
+
+
+def test_contingency_counts_out_of_range_labels(engine):
+    a = torch.tensor([0, 1, 2, 5, -1, 1], dtype=torch.int32).cuda()
+    b = torch.tensor([0, 1, 0, 0, 0, 9], dtype=torch.int32).cuda()
+    table, bad = engine.K.contingency(a, b, 3, 2)
+    assert int(bad.item()) == 3
+    assert table.cpu().tolist() == [[1, 0], [0, 1], [1, 0]]

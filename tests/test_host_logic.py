@@ -154,3 +154,40 @@ def test_get_clusters_parsing(capsys):
     assert prep.get_clusters(4) == [4]
     assert prep.get_clusters('6-2') is None and prep.get_clusters('abc') is None
     assert 'incorrent value for clusters' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('name,excl', [('testmode_500x512', False), ('testmode_500x512_excl', True)])
+def test_test_grouping_host_logic(tmp_path, golden_dir, capsys, eng, name, excl):
+    """test_grouping through the drop-in module on the stand-in back end: console text and classification log equal
+    the real reference's (tests/golden, oracle/make_golden.py:golden_testmode)."""
+    import json
+    import os
+    import os.path as osp
+    from videotofaces_b200.synth import eval_case
+    from videotofaces_b200 import grouping as vgrouping, runtime
+    X, R, gt = eval_case(excl)
+    fdir = tmp_path / 'faces'
+    os.makedirs(fdir)
+    paths = [str(fdir / ('f%06d.jpg' % i)) for i in range(X.shape[0])]
+    with open(tmp_path / 'labels.txt', 'w') as f:
+        f.write('\n'.join(str(int(g)) for g in gt) + '\n')
+    refs = [('c%02d' % i, ['unused.jpg']) for i in range(R.shape[0])]
+    runtime.reset_engine(eng)
+    try:
+        vgrouping.test_grouping(paths, refs, ('live', 'facenet_vgg', 'cpu', str(tmp_path), excl, 16, None, 0.97, 0), X=X, R=R)
+    finally:
+        runtime.reset_engine(None)
+    with open(osp.join(golden_dir, 'MANIFEST.json')) as f:
+        assert capsys.readouterr().out == json.load(f)['cases'][name]['stdout']
+    with open(fdir / 'log_classification.csv') as f, open(osp.join(golden_dir, name + '.log_classification.csv')) as g:
+        assert f.read() == g.read()
+
+
+def test_rand_score_host_arithmetic(eng):
+    import sklearn.metrics
+    rng = np.random.default_rng(3)
+    for n, ka, kb in [(1000, 5, 5), (17, 3, 9), (4000, 40, 2)]:
+        a, b = rng.integers(0, ka, n) * 2 + 1, rng.integers(0, kb, n).astype(np.int32)
+        assert eng.rand_score(a, torch.from_numpy(b)) == sklearn.metrics.rand_score(a, b)
+    assert eng.rand_score(np.arange(6), torch.arange(6, dtype=torch.int32)) == 1.0      # every row its own cluster
+    assert eng.rand_score(np.zeros(6, int), torch.zeros(6, dtype=torch.int32)) == 1.0   # nothing split

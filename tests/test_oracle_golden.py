@@ -9,7 +9,7 @@ import pytest
 
 from oracle import reference_calls as RC
 from oracle import restatement as RS
-from videotofaces_b200.synth import blobs, plant_dupes
+from videotofaces_b200.synth import blobs, eval_case, plant_dupes
 
 
 def _gold(golden_dir, name):
@@ -168,3 +168,25 @@ def test_kmeanspp_restatement_trace_known_answer():
     for k in (2, 5):
         idx, _ = RS.kmeans_plusplus(Xc, k, 0)
         assert np.array_equal(idx, RC.kmeanspp_indices(X, k, 0))
+
+
+@pytest.mark.parametrize('name,excl', [('testmode_500x512', False), ('testmode_500x512_excl', True)])
+def test_testmode_calls_match_reference(golden_dir, name, excl):
+    """test_grouping (grouping.py:140-155): the oracle's call sequence and the rand_score restatement reproduce the line
+    the real reference printed."""
+    import json
+    with open(osp.join(golden_dir, 'MANIFEST.json')) as f:
+        want = json.load(f)['cases'][name]['stdout']
+    X, R, gt = eval_case(excl)
+    if excl:
+        keep = gt != gt.max()
+        X, gt = X[keep], gt[keep]
+    acc, rnd, sil, labels = RC.testmode_scores(X, R, gt, int(gt.max()), None if excl else 0.97, 0)
+    assert '%.4f / %.4f / %.4f' % (acc, rnd, sil) in want
+    assert RS.rand_score(gt, labels) == rnd
+    assert RS.rand_score(gt, gt) == 1.0 and RS.rand_score(np.zeros(5), np.zeros(5)) == 1.0
+    rng = np.random.default_rng(0)
+    import sklearn.metrics
+    for _ in range(5):
+        a, b = rng.integers(0, 7, 1000) * 3 - 4, rng.integers(0, 4, 1000)
+        assert RS.rand_score(a, b) == sklearn.metrics.rand_score(a, b)

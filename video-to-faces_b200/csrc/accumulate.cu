@@ -324,3 +324,47 @@ extern "C" int vtf_lloyd_update(const double* sums, const int64_t* counts, const
     VTF_CHECK_LAST("vtf_lloyd_update");
     return VTF_OK;
 }
+
+namespace vtf {
+
+// ---- contingency table of two labellings (sklearn.metrics.cluster.contingency_matrix, the input of rand_score's pair
+// confusion matrix, SK/metrics/cluster/_supervised.py:195-271): out[a[i] * nb + b[i]] += 1.  Shared-memory histogram per
+// CTA when the table fits (na*nb <= kContBins), global atomics otherwise; labels outside [0,na) x [0,nb) are counted in
+// *bad so that the host can refuse them.
+constexpr int kContBins = 8192;
+__global__ void __launch_bounds__(256) contingency_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t N,
+                                                          int na, int nb, unsigned long long* __restrict__ out,
+                                                          unsigned long long* __restrict__ bad) {
+    __shared__ unsigned int hist[kContBins];
+    const int bins = na * nb;
+    const bool local = bins <= kContBins;
+    if (local) { for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = 0u; __syncthreads(); }
+    unsigned int nbad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = __ldg(a + i), y = __ldg(b + i);
+        if ((unsigned)x >= (unsigned)na || (unsigned)y >= (unsigned)nb) { ++nbad; continue; }
+        if (local) atomicAdd(&hist[x * nb + y], 1u);
+        else atomicAdd(&out[(size_t)x * nb + y], 1ull);
+    }
+    if (nbad) atomicAdd(bad, (unsigned long long)nbad);
+    if (local) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < bins; i += blockDim.x) { const unsigned int v = hist[i]; if (v) atomicAdd(&out[i], (unsigned long long)v); }
+    }
+}
+
+}  // namespace vtf
+
+extern "C" int vtf_contingency(const int32_t* a, const int32_t* b, int64_t N, int na, int nb, int64_t* table, int64_t* bad,
+                               void* stream) {
+    VTF_REQUIRE(a && b && table && bad && N >= 0 && na > 0 && nb > 0 && (int64_t)na * nb <= (1 << 26), "vtf_contingency");
+    VTF_CUDA(cudaMemsetAsync(table, 0, (size_t)na * nb * sizeof(int64_t), (cudaStream_t)stream), "vtf_contingency");
+    VTF_CUDA(cudaMemsetAsync(bad, 0, sizeof(int64_t), (cudaStream_t)stream), "vtf_contingency");
+    if (N == 0) return VTF_OK;
+    // per-CTA rows cap at 2^32-1 increments per bin: N / grid < 2^32 always holds for grid >= 1 and N < 2^40
+    const int64_t want = (N + 255) / 256;
+    const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+    VTF_LAUNCH(contingency_kernel, grid, 256, 0, stream, a, b, N, na, nb, (unsigned long long*)table, (unsigned long long*)bad);
+    VTF_CHECK_LAST("vtf_contingency");
+    return VTF_OK;
+}

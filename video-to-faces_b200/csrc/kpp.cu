@@ -196,10 +196,20 @@ __global__ void __launch_bounds__(kScanThreads) kpp_pick_scan_kernel(const float
         s_S = S0; s_t = t0;
     }
     __syncthreads();
+    // the next tile's elements wait in registers while the current one is scanned (one CTA cannot hide HBM latency otherwise)
+    float nxt[kScanPer];
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) { const int64_t g = (int64_t)k * kScanThreads + tid; nxt[k] = g < N ? __ldg(closest + g) : 0.f; }
     for (int64_t base = 0; base < N; base += kScanTile) {
         if (s_t >= T && total_out == nullptr) break;                   // every threshold placed (uniform: s_t is shared)
         const int n = (int)min((int64_t)kScanTile, N - base);
-        for (int i = tid; i < kScanTile; i += kScanThreads) tile[i] = (i < n) ? __ldg(closest + base + i) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) tile[k * kScanThreads + tid] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            const int64_t g = base + kScanTile + (int64_t)k * kScanThreads + tid;
+            nxt[k] = g < N ? __ldg(closest + g) : 0.f;
+        }
         __syncthreads();
         int pos = 0;
         while (pos < n) {
@@ -326,6 +336,42 @@ static int kpp_grid() { return num_sms() * 4; }
 
 using namespace vtf;
 
+
+// ---- round glue: everything SK/cluster/_kmeans.py:249-266 does between two distance passes, on the device, so that a
+// k-means++ round needs no host round trip.  One thread; T <= kMaxTrials.
+//   in : pots[n_pots]  fp64 potentials of the previous round's candidates (n_pots = 1 after the first centre)
+//        u[T]          the round's uniform draws (host MT19937, drawn in advance: they do not depend on the data)
+//   out: best          argmin of the fp32-rounded potentials (first minimum, np.argmin), :266
+//        thr[T]        ascending fp32 thresholds = smallest fp32 >= u * pot (searchsorted compares the fp32 cumsum with
+//                      fp64 values, :249-250), order[T] = draw index of each sorted threshold
+__global__ void kpp_round_prep_kernel(const double* __restrict__ pots, int n_pots, const double* __restrict__ u, int T,
+                                      float* __restrict__ thr, int* __restrict__ order, int64_t* __restrict__ best) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int b = 0;
+    float pot = (float)pots[0];
+    for (int i = 1; i < n_pots; ++i) {
+        const float p = (float)pots[i];
+        if (p < pot) { pot = p; b = i; }
+    }
+    if (best) *best = b;
+    for (int t = 0; t < T; ++t) {
+        const double v = u[t] * (double)pot;
+        float f = __double2float_rn(v);
+        if ((double)f < v) f = nextafterf(f, INFINITY);
+        int j = t;                                               // stable insertion sort
+        while (j > 0 && thr[j - 1] > f) { thr[j] = thr[j - 1]; order[j] = order[j - 1]; --j; }
+        thr[j] = f;
+        order[j] = t;
+    }
+}
+
+// cand[order[t]] = picked[t], never-reached thresholds clip to N-1 (_kmeans.py:254)
+__global__ void kpp_unsort_kernel(const int64_t* __restrict__ picked, const int* __restrict__ order, int T, int64_t N,
+                                  int64_t* __restrict__ cand) {
+    const int t = threadIdx.x;
+    if (t < T) cand[order[t]] = picked[t] < 0 ? N - 1 : picked[t];
+}
+
 extern "C" {
 
 size_t vtf_kpp_ws_bytes(int T) { return (size_t)kpp_grid() * (size_t)(T > 0 ? T : 1) * sizeof(double); }
@@ -361,6 +407,21 @@ int vtf_kpp_pick(const float* closest, int64_t N, const float* thr, int T, const
     if (serial) VTF_LAUNCH(kpp_pick_kernel, 1, 128, 0, stream, closest, N, thr, T, offset_in, total_out, idx);
     else VTF_LAUNCH(kpp_pick_scan_kernel, 1, kScanThreads, 0, stream, closest, N, thr, T, offset_in, total_out, idx);
     VTF_CHECK_LAST("vtf_kpp_pick");
+    return VTF_OK;
+}
+
+int vtf_kpp_round_prep(const double* pots, int n_pots, const double* u, int T, float* thr, int32_t* order, int64_t* best,
+                       void* stream) {
+    VTF_REQUIRE(pots && u && thr && order && n_pots > 0 && T > 0 && T <= kMaxTrials, "vtf_kpp_round_prep");
+    VTF_LAUNCH(kpp_round_prep_kernel, 1, 32, 0, stream, pots, n_pots, u, T, thr, order, best);
+    VTF_CHECK_LAST("vtf_kpp_round_prep");
+    return VTF_OK;
+}
+
+int vtf_kpp_unsort(const int64_t* picked, const int32_t* order, int T, int64_t N, int64_t* cand, void* stream) {
+    VTF_REQUIRE(picked && order && cand && T > 0 && T <= kMaxTrials && N > 0, "vtf_kpp_unsort");
+    VTF_LAUNCH(kpp_unsort_kernel, 1, 32, 0, stream, picked, order, T, N, cand);
+    VTF_CHECK_LAST("vtf_kpp_unsort");
     return VTF_OK;
 }
 

@@ -24,6 +24,9 @@ SIGNATURES = {
     'vtf_kpp_ws_bytes': (c_sz, [c_int]),
     'vtf_kpp_dist': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_kpp_pick': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_contingency': (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    'vtf_kpp_round_prep': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_kpp_unsort': (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     'vtf_kpp_pick_serial': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vtf_lloyd_assign': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vtf_cluster_sums_ws_bytes': (c_sz, [c_int, c_int]),

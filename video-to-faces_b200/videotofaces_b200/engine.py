@@ -88,7 +88,8 @@ class GroupingEngine:
     def to_device(self, A, dtype=torch.float32):
         if isinstance(A, torch.Tensor):
             return A.to(device=self.device, dtype=dtype).contiguous()
-        A = np.ascontiguousarray(A, dtype={torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64}[dtype])
+        A = np.ascontiguousarray(A, dtype={torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32,
+                                           torch.int64: np.int64}[dtype])
         return torch.from_numpy(A).to(self.device, non_blocking=False)
 
     def upload_replicated(self, A):
@@ -234,35 +235,28 @@ class GroupingEngine:
         trials = n_local_trials(k)
         # rs.choice(N, p=uniform) consumes one random_sample() and picks searchsorted(cdf, u, 'right')
         first = min(int(rs.random_sample() * N), N - 1)                        # _kmeans.py:231
-        seeds = [first]
+        # the uniform draws of every round (_kmeans.py:249) do not depend on the data: draw them all now, in the
+        # reference's order, and keep the rounds themselves on the device -- no host round trip until the end
+        U = self.to_device(np.stack([rs.uniform(size=trials) for _ in range(1, k)]).reshape(max(k - 1, 0), trials),
+                           torch.float64) if k > 1 else None
         closest = K.empty((N,), torch.float32)
         out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None)     # _kmeans.py:240
-        closest[b:e] = out[0]
-        comm.allgather_rows(closest, ctx.bounds)
-        comm.allreduce_sum(pots)
-        pot = np.float32(pots.cpu().numpy()[0])                                # _kmeans.py:243
-        picks = []                                                             # (candidate ids on device, winner) per round
-        for _ in range(1, k):
-            rand_vals = rs.uniform(size=trials) * np.float64(pot)              # _kmeans.py:249
-            thr = _ceil_to_f32(rand_vals)
-            order = np.argsort(thr, kind='stable')
-            inv = np.empty_like(order)
-            inv[order] = np.arange(trials)
-            picked = K.kpp_pick(closest, torch.from_numpy(thr[order]).to(self.device))
-            # back to draw order, never-reached thresholds clip to N-1 (_kmeans.py:254): all on the device, no sync
-            cand_t = picked[torch.from_numpy(inv).to(self.device)]
-            cand_t = torch.where(cand_t < 0, torch.full_like(cand_t, N - 1), cand_t)
-            out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand_t), closest[b:e])   # :257-263
-            comm.allreduce_sum(pots)
-            pots32 = pots.cpu().numpy().astype(np.float32)                     # the one D2H of the round
-            best = int(np.argmin(pots32))                                      # _kmeans.py:266
-            pot = pots32[best]
-            closest[b:e] = out[best]
+        chosen = []
+        for r in range(k - 1):
+            comm.allreduce_sum(pots)                                           # _kmeans.py:243 / :263
+            thr, order, best = K.kpp_round_prep(pots, U[r])                    # :266 of the last round, :249 of this one
+            closest[b:e] = out.index_select(0, best)[0]                        # :272
             comm.allgather_rows(closest, ctx.bounds)
-            picks.append((cand_t, best))
-        if picks:
-            chosen = torch.stack([c[bst] for c, bst in picks]).cpu().numpy()
-            seeds.extend(int(v) for v in chosen)
+            if r > 0:
+                chosen.append(cand.index_select(0, best))                      # :270
+            cand = K.kpp_unsort(K.kpp_pick(closest, thr), order, N)            # :250-254
+            out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand), closest[b:e])      # :257-263
+        seeds = [first]
+        if k > 1:
+            comm.allreduce_sum(pots)
+            best = K.kpp_round_prep(pots, U[0])[2]                             # :266 (the last centre's distances are not needed)
+            chosen.append(cand.index_select(0, best))
+            seeds.extend(int(v) for v in torch.cat(chosen).cpu().numpy())      # the one D2H of the seeding
         return np.asarray(seeds, dtype=np.int64)
 
     # ------------------------------------------------------------------------------ a6 Lloyd
@@ -357,20 +351,13 @@ class GroupingEngine:
         Xs = ctx.Xc[b:e]
         active = (1 << nL) - 1
         n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
-        red = K.zeros((ktot * d + ktot + nL,), torch.float64)
         for it in range(max_iter):
-            counts = K.zeros((ktot,), torch.int64)
-            changed = K.zeros((nL,), torch.int64)
+            cc = K.zeros((ktot + nL,), torch.int64)                            # counts | changed: one memset, one all-reduce
+            counts, changed = cc[:ktot], cc[ktot:]
             K.lloyd_assign_multi(Xs, C_all, off, active, labels_all, b, counts, changed)
             sums = K.cluster_sums_multi(Xs, labels_all, b, off, active)
-            if comm.active:
-                red[:ktot * d] = sums.view(-1)
-                red[ktot * d:ktot * d + ktot] = counts.to(torch.float64)
-                red[ktot * d + ktot:] = changed.to(torch.float64)
-                comm.allreduce_sum(red)
-                sums = red[:ktot * d].view(ktot, d).clone()
-                counts = red[ktot * d:ktot * d + ktot].round().to(torch.int64)
-                changed = red[ktot * d + ktot:].round().to(torch.int64)
+            comm.allreduce_sum(sums)
+            comm.allreduce_sum(cc)
             C_new, _, stats = K.lloyd_update_multi(sums, counts, changed, off, active, C_all, stride)
             st = stats.cpu().numpy()                                           # the one D2H of the iteration
             for L in range(nL):
@@ -642,6 +629,52 @@ class GroupingEngine:
                 K.sil_finish_cells(cellsum, c2c[j], k, perm, lab, cnt, rb0 * 128, rb1 * 128, out[j:j + 1])
             comm.allreduce_sum(out)
         return (out / ctx.N).cpu().numpy().tolist()
+
+    # ------------------------------------------------------------------------------ f3 rand score
+    def rand_score(self, labels_true, labels_pred):
+        """sklearn.metrics.rand_score (SK/metrics/cluster/_supervised.py:280-357) from the contingency table
+        (:106-192) and the pair confusion matrix (:195-271).  `labels_true` is a host vector of arbitrary integers
+        (labels.txt of test_grouping); `labels_pred` a label vector on the device or host.  The O(N) histogram runs
+        on the device, row-sharded; the k x k integer arithmetic that follows stays on the host, in Python integers
+        (the reference's int64 would overflow beyond 3 x 10^9 rows; below that the results are identical)."""
+        K, comm = self.K, self.comm
+        gt = np.asarray(labels_true)
+        if gt.ndim != 1:
+            raise ValueError('labels_true must be 1D: shape is %r' % (gt.shape,))          # check_clusterings, :34-77
+        classes, inv = np.unique(gt, return_inverse=True)
+        pred = labels_pred if isinstance(labels_pred, torch.Tensor) else torch.from_numpy(np.asarray(labels_pred))
+        if pred.dim() != 1:
+            raise ValueError('labels_pred must be 1D: shape is %r' % (tuple(pred.shape),))
+        N = gt.shape[0]
+        if pred.numel() != N:
+            raise ValueError('Found input variables with inconsistent numbers of samples: %r' % [N, pred.numel()])
+        pred = pred.to(self.device)
+        if N == 0:
+            return 1.0
+        # np.unique of the predicted labels: KMeans labels are 0..k-1 but some may be unused; the table only needs
+        # an upper bound, empty columns contribute nothing to any sum
+        lo, hi = int(pred.min().item()), int(pred.max().item())
+        pred32 = (pred - lo).to(torch.int32).contiguous()
+        a = self.to_device(inv.astype(np.int32), torch.int32)
+        b, e = self._my_rows(N)
+        table, bad = K.contingency(a[b:e], pred32[b:e], len(classes), hi - lo + 1)
+        both = torch.cat([table.view(-1), bad])
+        comm.allreduce_sum(both)
+        h = both.cpu().numpy()
+        if h[-1] != 0:
+            raise RuntimeError('contingency: %d labels out of range' % int(h[-1]))
+        T = [[int(v) for v in row] for row in h[:-1].reshape(len(classes), hi - lo + 1)]
+        n_c = [sum(row) for row in T]
+        n_k = [sum(col) for col in zip(*T)]
+        sum_squares = sum(v * v for row in T for v in row)
+        c11 = sum_squares - N
+        c01 = sum(v * n_k[j] for row in T for j, v in enumerate(row)) - sum_squares
+        c10 = sum(v * n_c[i] for i, row in enumerate(T) for v in row) - sum_squares
+        c00 = N * N - c01 - c10 - sum_squares
+        num, den = c00 + c11, c00 + c01 + c10 + c11
+        if num == den or den == 0:
+            return 1.0
+        return float(np.int64(num) / np.int64(den)) if den < (1 << 63) else num / den
 
     def cluster_scores(self, ctx, results, force=None):
         """grouping.py:104-108: [(k, silhouette, CH, DB)] for the KMeans results of a sweep."""

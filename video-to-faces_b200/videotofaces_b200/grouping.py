@@ -107,3 +107,55 @@ def cluster_faces(paths, X, cluster_params):
     print()
     for p in paths:
         os.remove(p)
+
+
+def get_ground_truths(paths, out_dir, exclude_other):
+    """grouping.py:158-172: 1-based class numbers, one per line of <out_dir>/labels.txt; the highest number is the
+    'other' class when `exclude_other` is set; the number of clusters is the highest remaining number."""
+    try:
+        with open(osp.join(out_dir, 'labels.txt')) as f:
+            gt = np.asarray([int(x) for x in f.read().splitlines()])
+    except Exception:  # noqa: BLE001  (the reference catches everything here, grouping.py:162)
+        raise ValueError('Could not load ground truth labels for testing.'
+                         'Expecting file "labels.txt" inside out_dir, filled with line-separated integers')
+    keep = None
+    if exclude_other:
+        other_class = max(gt)
+        keep = gt != other_class
+        print('Excluded %u images with "other" class' % np.count_nonzero(~keep))
+        paths = [f for f, kp in zip(paths, keep) if kp]
+        gt = gt[keep]
+    return gt, paths, max(gt), keep
+
+
+def grouping_test_scores(X, R, gt, n_clusters, thr, rstate, classes=None, log=False, paths=None, out_dir=None):
+    """The three numbers of test_grouping (grouping.py:146-152) on embeddings that are already there:
+    classification accuracy against 1-based ground truth, rand score and silhouette score of one KMeans fit."""
+    eng = get_engine()
+    classes = list(classes) if classes is not None else [str(i) for i in range(R.shape[0])]
+    inds, _ = classify(X, R, classes, thr, log, paths, out_dir)                # grouping.py:146
+    acc = np.count_nonzero(inds + 1 == gt) / gt.size                           # grouping.py:147
+    ctx, results = eng.kmeans_sweep(X, [int(n_clusters)], rstate)              # grouping.py:149
+    rand_scr = eng.rand_score(gt, results[0].labels)                           # grouping.py:150
+    silh_scr = eng.silhouette_scores(ctx, [results[0].labels], [results[0].k], [results[0].counts])[0]   # :151
+    return acc, rand_scr, float(np.float32(silh_scr)), results[0]
+
+
+def test_grouping(paths, refs, test_params, X=None, R=None):
+    """grouping.py:140-155.  The encoder networks are outside this package: `X` / `R` hand the embeddings of `paths`
+    (all of them, before the 'other' exclusion) and of the first image of every class over directly; without them
+    the upstream encoders are used when that package is importable."""
+    style, mname, device, out_dir, exclude_other, bs, area, thr, rstate = test_params
+    gt, paths, n_clusters, keep = get_ground_truths(paths, out_dir, exclude_other)
+    if X is None or R is None:
+        from videotofaces.grouping import get_encoder_model, encode_faces    # the unmodified reference package
+        model = get_encoder_model(style, mname, device)
+        X = encode_faces(paths, model, bs, area)
+        R = encode_refs(refs, model)
+    elif keep is not None:
+        X = np.asarray(X)[keep]
+    acc, rand_scr, silh_scr, _ = grouping_test_scores(X, R, gt, n_clusters, None if exclude_other else thr, rstate,
+                                                      classes=[c for (c, _) in refs], log=True, paths=paths, out_dir=out_dir)
+    print('%.4f / %.4f / %.4f' % (acc, rand_scr, silh_scr))
+    print('classification accuracy / rand score for clustering / silhouette score for clustering')
+test_grouping.__test__ = False                    # a reference entry point, not a pytest test

@@ -88,6 +88,29 @@ class CudaKernels:
                 None, ptr(total), ptr(idx), stream())
         return (idx, total) if want_total else idx
 
+    def kpp_round_prep(self, pots, u):
+        """(thr sorted fp32 [T], order int32 [T], best int64 [1]) from the previous potentials and this round's draws."""
+        T = u.numel()
+        thr = self.empty((T,), torch.float32)
+        order = self.empty((T,), torch.int32)
+        best = self.empty((1,), torch.int64)
+        nv.call('vtf_kpp_round_prep', ptr(pots), c_int(pots.numel()), ptr(u), c_int(T), ptr(thr), ptr(order), ptr(best),
+                stream())
+        return thr, order, best
+
+    def kpp_unsort(self, picked, order, N):
+        cand = self.empty((picked.numel(),), torch.int64)
+        nv.call('vtf_kpp_unsort', ptr(picked), ptr(order), c_int(picked.numel()), c_i64(N), ptr(cand), stream())
+        return cand
+
+    # ------------------------------------------------------------------ f3
+    def contingency(self, a, b, na, nb):
+        """(table int64 [na, nb], bad int64 [1]) for two int32 label vectors of equal length."""
+        table = self.empty((na, nb), torch.int64)
+        bad = self.empty((1,), torch.int64)
+        nv.call('vtf_contingency', ptr(a), ptr(b), c_i64(a.numel()), c_int(na), c_int(nb), ptr(table), ptr(bad), stream())
+        return table, bad
+
     # ------------------------------------------------------------------ a6
     def lloyd_assign(self, Xc, C, labels, counts, n_changed):
         N, d = self._chk(Xc)

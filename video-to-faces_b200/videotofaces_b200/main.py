@@ -9,7 +9,7 @@ import os.path as osp
 import numpy as np
 
 from .prep import validate_args, get_clusters, get_class_ref, get_paths_for_grouping
-from .grouping import cluster_faces, classify_faces
+from .grouping import cluster_faces, classify_faces, test_grouping
 from .dupes import remove_dupes_overall
 
 
@@ -55,16 +55,24 @@ def video_to_faces(input_path=None, input_ext=None,
         out_dir = input_path if osp.isdir(input_path) else osp.dirname(osp.abspath(input_path))
 
     refs = None
-    if group_mode == 'clustering':                                             # main.py:41-44
+    if group_mode == 'clustering' or _test_enc:                                # main.py:41-44
         clusters = get_clusters(clusters)
         if not clusters:
             return
-    if group_mode == 'classification':                                         # main.py:45-48
+    if group_mode == 'classification' or _test_enc:                            # main.py:45-48
         refs = get_class_ref(ref_dir, out_dir)
         if not refs:
             return
     imgpaths = get_paths_for_grouping(out_dir)                                 # main.py:49-52
     if not imgpaths:
+        return
+
+    if _test_enc:                                                              # main.py:65-69
+        test_params = (style, enc_model, device, out_dir, _test_exclude_other, enc_batch_size, enc_area, enc_oth_thr,
+                       random_state)
+        X = _load_features(features) if features is not None else None
+        R = _load_features(ref_features) if ref_features is not None else None
+        test_grouping(imgpaths, refs, test_params, X=X, R=R)
         return
 
     encoder = None

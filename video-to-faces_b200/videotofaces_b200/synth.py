@@ -29,6 +29,24 @@ def blobs(N, d, kc=8, noise=1.0, seed=0, normalize=True):
     return np.ascontiguousarray(X, dtype=np.float32)
 
 
+def blob_truth(N, d, kc=8, seed=0, normalize=True):
+    """(centres [kc,d], blob index of every row [N]) of blobs(N, d, kc, ., seed): the first two draws of the same
+    generator, for tests that need ground-truth classes (test_grouping's labels.txt and reference embeddings)."""
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((kc, d), dtype=np.float32)
+    ids = rng.integers(0, kc, N)
+    return (_normalize_rows(C) if normalize else C), ids.astype(np.int64)
+
+
+def eval_case(exclude_other):
+    """(X, R, labels.txt numbers) of the two test_grouping golden cases (oracle/make_golden.py:testmode_cases): five
+    heavily overlapping blobs, reference embeddings = jittered blob centres, ground truth = blob number (1-based)."""
+    C, ids = blob_truth(500, 512, kc=5, seed=4)
+    X = blobs(500, 512, kc=5, noise=5.0, seed=4)
+    R = (C + np.float32(0.15) * np.random.default_rng(9).standard_normal(C.shape, dtype=np.float32)).astype(np.float32)
+    return X, (np.ascontiguousarray(R[:4]) if exclude_other else R), ids + 1
+
+
 def plant_dupes(X, frac=50, seed=1, normalize=True):
     """Plant m = N/frac near-duplicates: sources in rows < N/2, targets in rows >= N/2.
 
