@@ -209,7 +209,8 @@ def main():
     sampler.join(timeout=2)
 
     # dominant kernel: the tcgen05 silhouette sweep, timed by CUDA events on its launch stream
-    sweeps = [(a.elapsed_time(b), flops) for (name, a, b, flops) in eng.events if name == 'sil_sweep']
+    sweeps = [(a.elapsed_time(b), flops() if callable(flops) else flops) for (name, a, b, flops) in eng.events
+              if name == 'sil_sweep']
     pk = peaks()
     roof = None
     traffic = None
@@ -222,7 +223,7 @@ def main():
         pass
     if sweeps:
         t_ms = float(np.mean([t for t, _ in sweeps]))
-        flops = sweeps[0][1]
+        flops = float(np.mean([f for _, f in sweeps]))
         ach = flops / (t_ms * 1e-3) / 1e12
         full_gram = 2.0 * float(((N + 255) // 256) * 256) ** 2 * d
         roof = dict(bound='tensor', kernel='sil_sweep_kernel (tcgen05 cta_group::2 kind::f16, fp32 accumulate in TMEM)', achieved=ach,

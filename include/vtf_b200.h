@@ -201,10 +201,14 @@ int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, float scale
 /* Symmetric form (D_pq = D_qp): only tiles on or above the diagonal are computed -- half the MMAs -- and every
  * off-diagonal block also feeds the row sums of its columns (warp transpose-reduce in the epilogue).  Rank r of
  * `world` sweeps unit pairs (q, U-1-q), q = r, r + world, ... (U = P/256 units of 256 rows); each rank's cellsum
- * then holds partial sums for ALL rows and the caller adds them (all-reduce) before vtf_sil_finish_cells.     */
+ * then holds partial sums for ALL rows and the caller adds them (all-reduce) before vtf_sil_finish_cells.
+ * work_counter != NULL switches to the DYNAMIC schedule: the pairs are cut into sub-ranges and every CTA pair of every
+ * rank claims the next one with an atomicAdd (system scope) on *work_counter, which must be 0 before the first rank
+ * starts and is shared by all ranks (vtf_shared_alloc on one rank, vtf_shared_open on the others: the claims travel
+ * over NVLink).  A slower GPU then simply takes fewer items.  tiles_done (nullable) += 256 x 256 tiles computed here. */
 int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int d, float scale,
-                      const int32_t* chunk_cell, int n_cells, int rank, int world,
-                      float* cellsum, void* stream);
+                      const int32_t* chunk_cell, int n_cells, int rank, int world, float* cellsum,
+                      uint32_t* work_counter, uint64_t* tiles_done, void* stream);
 /* finish: for labelling l (k_l clusters), per real row: a = S_own/(n_own-1),
  * b = min_{c != own} S_c/n_c, s = (b-a)/max(a,b) (0 for singleton clusters, :323), and
  * out[l] += sum_i s_i in fp64.  From the exact path: vtf_sil_finish_rows on rowsum[N,k].    */
@@ -224,6 +228,15 @@ int vtf_sil_finish_cells(const float* cellsum, int64_t P, int n_cells,
  * anything else is counted in *bad.  Shards add across ranks.                                          */
 int vtf_contingency(const int32_t* a, const int32_t* b, int64_t N, int na, int nb, int64_t* table, int64_t* bad,
                     void* stream);
+
+/* ---- device memory shared between the ranks of one node (CUDA IPC; the sweep's work counter) ------------------
+ * alloc: cudaMalloc + zero + export a 64-byte handle (owner rank).  open: map another process's allocation (peer
+ * access over NVLink is enabled on first use).  zero: stream-ordered memset, valid on owner and opened pointers.   */
+int vtf_shared_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int vtf_shared_open(const unsigned char handle[64], void** ptr);
+int vtf_shared_zero(void* ptr, size_t bytes, void* stream);
+int vtf_shared_close(void* ptr);
+int vtf_shared_free(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -251,7 +251,7 @@ class FakeKernels:
         for c in range(n_cells):
             cellsum[c, rows[0]:rows[-1] + 1] += torch.from_numpy(D[:, cc == c].sum(1, dtype=np.float32))
 
-    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum):
+    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum, counter=None, tiles_done=None):
         """Upper-triangle sweep: unit pairs (q, U-1-q) of 256 rows; off-diagonal tiles feed rows and columns."""
         f = _np(Xh).astype(np.float32)
         m = _np(aug)

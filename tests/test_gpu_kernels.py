@@ -330,6 +330,40 @@ def test_symmetric_sweep_matches_full_sweep(engine, N, d, ks):
         np.testing.assert_allclose(sym, want, rtol=1e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize('N,d', [(40000, 512), (9000, 768), (300, 64)])
+def test_dynamic_schedule_computes_every_tile_once(engine, N, d):
+    """Work items claimed from the shared counter (the default) against the static round-robin list: same sums, and the
+    launch reports exactly U(U+1)/2 tiles -- nothing skipped, nothing done twice."""
+    K = engine.K
+    X = blobs(N, d, kc=4, seed=5, normalize=(d == 512))
+    ctx = engine.prepare(X)
+    ks = [2, 5]
+    rng = np.random.default_rng(1)
+    labels = [dev(rng.integers(0, k, N).astype(np.int32)) for k in ks]
+    perm, chunk_cell, c2c, G, P = engine.build_cells(labels, ks)
+    Xc = engine._pad16(ctx.Xc, 64)
+    scale, shift, pad_m = engine.sil_scale(Xc)
+    Xh, aug = K.sil_pack(Xc, perm, P, scale, shift, pad_m)
+    U = P // 256
+    out = []
+    for dynamic in (False, True, True):
+        cellsum = K.zeros((G, P), torch.float32)
+        tiles = K.zeros((1,), torch.int64)
+        counter = K.zeros((1,), torch.int32)
+        K.sil_sweep_sym(Xh, aug, scale, chunk_cell, G, 0, 1, cellsum, counter.data_ptr() if dynamic else None, tiles)
+        assert int(tiles.item()) == U * (U + 1) // 2
+        if dynamic:
+            assert int(counter.item()) >= 1                      # items were claimed from the counter
+        out.append(cellsum.double().cpu().numpy())
+    np.testing.assert_allclose(out[1], out[0], rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(out[2], out[0], rtol=2e-5, atol=1e-3)
+    engine.dynamic = False
+    a = engine.silhouette_scores(ctx, labels, ks, force='tc')
+    engine.dynamic = True
+    b = engine.silhouette_scores(ctx, labels, ks, force='tc')
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
 def test_sweep_rejects_bad_shapes(K):
     from videotofaces_b200 import _native
     with pytest.raises(_native.NativeError):

@@ -34,6 +34,7 @@ def main():
     ap.add_argument('--dim', type=int, default=512)
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--sym', action='store_true', help='time vtf_sil_sweep_sym (upper triangle) instead of the full sweep')
+    ap.add_argument('--modes', default='static', help='--sym only: comma list of static,dynamic (work counter) per library')
     args = ap.parse_args()
     from videotofaces_b200.runtime import get_engine
     from videotofaces_b200._native import c_f32, c_i64, c_int, c_vp
@@ -60,20 +61,26 @@ def main():
         lib.vtf_sil_sweep.argtypes = [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]
         if args.sym:
             lib.vtf_sil_sweep_sym.restype = c_int
-            lib.vtf_sil_sweep_sym.argtypes = [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp]
-        libs.append((osp.basename(path), lib))
+            lib.vtf_sil_sweep_sym.argtypes = [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
+        for mode in (args.modes.split(',') if args.sym else ['static']):
+            libs.append((osp.basename(path) + ':' + mode, lib))
     cellsum = torch.zeros((G, P), dtype=torch.float32, device='cuda')
+    counter = torch.zeros(4, dtype=torch.int32, device='cuda')
+    tiles = torch.zeros(1, dtype=torch.int64, device='cuda')
     stream = c_vp(torch.cuda.current_stream().cuda_stream)
     results = {n: [] for n, _ in libs}
     ref = None
     for rep in range(args.reps + 1):
         for name, lib in libs:
             cellsum.zero_()
+            counter.zero_()
+            tiles.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if args.sym:
                 rc = lib.vtf_sil_sweep_sym(Xh.data_ptr(), aug.data_ptr(), P, d, scale, chunk_cell.data_ptr(), G, 0, 1,
-                                           cellsum.data_ptr(), stream)
+                                           cellsum.data_ptr(), counter.data_ptr() if name.endswith(':dynamic') else None,
+                                           tiles.data_ptr(), stream)
             else:
                 rc = lib.vtf_sil_sweep(Xh.data_ptr(), aug.data_ptr(), P, d, scale, chunk_cell.data_ptr(), G, 0, P // 128,
                                        cellsum.data_ptr(), stream)
@@ -85,6 +92,7 @@ def main():
             if ref is None:
                 ref = chk
             if rep > 0:
+                assert not args.sym or int(tiles.item()) == U * (U + 1) // 2, (name, int(tiles.item()), U * (U + 1) // 2)
                 results[name].append(dict(ms=a.elapsed_time(b), tflops=flops / a.elapsed_time(b) / 1e9, clk_after=clk,
                                           checksum_rel=abs(chk - ref) / abs(ref)))
     for name, r in results.items():

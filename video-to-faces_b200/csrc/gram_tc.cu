@@ -56,45 +56,49 @@ struct Params {
     int tiles_per_seg;   // 256-column tiles per segment
     int n_tiles;         // P / 256
     float flush_scale;   // sqrt(2) / scale: sqrt(max(-T, 0)) * flush_scale is the distance
-    int sym_rank;        // SYM: this rank sweeps unit pairs q = sym_rank, sym_rank + sym_world, ...
+    int sym_rank;        // SYM, static schedule: this rank takes items w = sym_rank, sym_rank + sym_world, ...
     int sym_world;
+    int chunk_tiles;     // SYM: tiles per column chunk (see next_work)
+    // SYM, dynamic schedule: work items are claimed one at a time from *work_counter (atomicAdd at system scope; with
+    // several ranks the counter lives in rank 0's memory and is reached over NVLink), so a slower GPU or SM pair simply
+    // claims fewer items.  nullptr = the static round-robin list.  n_items = all items of ALL ranks (SYM, both forms).
+    unsigned int* work_counter;
+    long long n_items;
+    unsigned long long* tiles_done;   // nullable: += number of 256 x 256 tiles this launch computed
 };
 
-// Work list shared by the three warp roles (they must walk it identically).
+// Work list shared by the three warp roles (they must walk it identically).  `w` = index of the work item.
 //   full sweep: item -> (row unit, column segment);  rbu = row unit (CPC row blocks), tiles [t0, t1)
 //   SYM (D is symmetric): only tiles on or above the diagonal are computed; a tile off the diagonal feeds the row
-//   sums of its rows AND, through a warp transpose-reduce, the row sums of its columns.  Unit u sweeps tiles
-//   u..U-1, so units are handed out in pairs (q, U-1-q) of constant total length U+1.
+//   sums of its rows AND, through a warp transpose-reduce, the row sums of its columns.  The triangle is cut into
+//   column CHUNKS of prm.chunk_tiles tiles (<= 32 MB of B operand, a quarter of the 126 MB L2) and walked chunk by
+//   chunk: item (c, u) = unit u against the tiles of chunk c at or right of the diagonal, items ordered c-major.
+//   CTA pairs that run at the same time therefore read the SAME chunk of B -- it comes from DRAM once and is then
+//   served by L2 for every unit -- and consecutive units start at different offsets inside the chunk (`o`, walked
+//   with wrap-around), so their column-sum REDs never hit the same addresses at the same time.  (History, same-box
+//   A/Bs: unit pairs (q, U-1-q) swept end to end, 330 GB of DRAM reads, 409-451 ms; the same cut into 4 sub-ranges
+//   and claimed dynamically, 509 ms -- four column regions in flight thrash L2; the lower triangle with every unit
+//   starting at column 0, 109 GB but 449 vs 425 ms because all pairs RED into the same columns at once.)
 template <bool PAIR, bool SYM>
-__device__ __forceinline__ bool next_work(const Params& prm, int64_t it, int64_t unit0, int64_t unit_stride,
-                                          int64_t& rbu, int& t0, int& t1) {
+__device__ __forceinline__ bool next_work(const Params& prm, int64_t w, int64_t& rbu, int& t0, int& t1, int& o) {
+    o = 0;
     if (SYM) {
-        // Unit pair (q, U-1-q) owns the virtual tile list [0, U+1): first the U-q tiles of unit q (t = q + i), then
-        // the q+1 tiles of unit U-1-q.  (Sweeping the LOWER triangle instead -- every unit starting at column tile 0,
-        // which shares B tiles in L2: 109 vs 328 GB of DRAM reads -- measured 5.5% SLOWER on the same box, 449 vs
-        // 425 ms: the column-sum REDs of all CTA pairs then hit the same addresses at the same time.)  Every pair has the same length, and each is cut into prm.n_seg equal
-        // sub-ranges so that the work items are small against the number of CTA pairs (tail effect); a sub-range
-        // that straddles the two units yields two pieces (it & 1), each with its own A block.
-        const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
-        const int64_t w = unit0 + (it >> 1) * unit_stride;             // sub-item of this rank
-        const int64_t q = prm.sym_rank + (w / prm.n_seg) * prm.sym_world;
-        if (q >= n_q) return false;
-        const int64_t ub = U - 1 - q;
-        const int64_t len_a = U - q, len_tot = (ub == q) ? len_a : U + 1;
-        const int64_t L = (len_tot + prm.n_seg - 1) / prm.n_seg;
-        const int64_t lo = (w % prm.n_seg) * L, hi = min(lo + L, len_tot);
-        if (!(it & 1)) {                                               // piece of unit q
-            rbu = q;
-            t0 = (int)(q + min(lo, len_a)); t1 = (int)(q + min(hi, len_a));
-        } else {                                                       // piece of unit U-1-q
-            rbu = ub;
-            t0 = (int)(ub + max(lo, len_a) - len_a); t1 = (int)(ub + max(hi, len_a) - len_a);
-        }
-        if (t1 < t0) t1 = t0;
+        if (w >= prm.n_items) return false;
+        const int64_t U = prm.n_rb / 2, TC = prm.chunk_tiles;
+        const int64_t nc_full = U / TC;                                 // chunks whose unit count is (c+1) * TC
+        int64_t c = (int64_t)((sqrt(8.0 * (double)w / (double)TC + 1.0) - 1.0) * 0.5);
+        c = min(max(c, (int64_t)0), nc_full);
+        while (c < nc_full && TC * (c + 1) * (c + 2) / 2 <= w) ++c;     // base(c+1) <= w
+        while (c > 0 && TC * c * (c + 1) / 2 > w) --c;                  // base(c) > w
+        const int64_t u = w - TC * c * (c + 1) / 2;
+        const int64_t lo = max(c * TC, u), hi = min((c + 1) * TC, U);
+        rbu = u;
+        t0 = (int)lo; t1 = (int)hi;
+        o = (int)(u % (hi - lo));
         return true;
     }
     const int64_t n_items = (prm.n_rb / (PAIR ? 2 : 1)) * prm.n_seg;
-    const int64_t item = unit0 + it * unit_stride;
+    const int64_t item = w;
     if (item >= n_items) return false;
     rbu = item / prm.n_seg;
     const int seg = (int)(item % prm.n_seg);
@@ -102,6 +106,25 @@ __device__ __forceinline__ bool next_work(const Params& prm, int64_t it, int64_t
     t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
     return true;
 }
+
+// Where the warp roles get their work item from.  Static: item = unit0 + seq * stride, computed by every role on its
+// own.  Dynamic (SYM with a work counter): lane 0 of the leader CTA's producer warp claims items with an atomicAdd and
+// publishes each one -- a word in an 8-deep ring in the shared memory of BOTH CTAs of the pair plus an mbarrier
+// arrive -- always one item ahead of its own use; every other role waits on that barrier and reads the word.  The
+// ring cannot be overrun: the producer is at most STAGES k-blocks ahead of the MMA warp, the MMA warp at most two
+// tiles ahead of the slowest epilogue warp, and every item has at least one tile, so all roles are within 4 items of
+// each other.  The first claimed index >= n_items is published too and ends every role's loop.
+struct Feed {
+    bool dyn;
+    uint32_t wfull0, wslot0;
+    int64_t unit0, stride;
+    int rank, world;                     // static list: ranks interleave item by item
+    __device__ __forceinline__ int64_t get(int64_t seq) const {
+        if (!dyn) return (unit0 + seq * stride) * world + rank;
+        mbar_wait_cluster(wfull0 + 8u * (uint32_t)(seq & 7), (uint32_t)((seq >> 3) & 1));
+        return (int64_t)ld_shared_u32(wslot0 + 4u * (uint32_t)(seq & 7));
+    }
+};
 
 // A_RESIDENT: the item's 128 x d A block is loaded once and kept; otherwise A k-blocks stream with B.
 // PAIR: two CTAs of a cluster (one SM pair) run one cta_group::2 MMA of 256 rows x 256 columns: each
@@ -134,6 +157,8 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto tfull_bar = [&](int s) { return a_empty + 8u + 8u * s; };
     auto tempty_bar = [&](int s) { return a_empty + 8u + 16u + 8u * s; };
     const uint32_t tmem_slot = a_empty + 8u + 32u;
+    const uint32_t wfull0 = tmem_slot + 8u;                  // dynamic schedule: 8 mbarriers + 8 words (see Feed)
+    const uint32_t wslot0 = wfull0 + 64u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,6 +168,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * CPC); }
+        for (int s = 0; s < 8; ++s) mbar_init(wfull0 + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -161,16 +187,39 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     static_assert(!SYM || PAIR, "the symmetric sweep runs on CTA pairs");
-    const int64_t unit0 = blockIdx.x / CPC, unit_stride = gridDim.x / CPC;
+    Feed feed;
+    feed.dyn = SYM && prm.work_counter != nullptr;
+    feed.wfull0 = wfull0; feed.wslot0 = wslot0;
+    feed.unit0 = blockIdx.x / CPC; feed.stride = gridDim.x / CPC;
+    feed.rank = SYM ? prm.sym_rank : 0; feed.world = SYM ? prm.sym_world : 1;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0, a_ph = 0;
+            int64_t w = 0, seq_pub = 0;
+            bool ended = false;
             for (int64_t it = 0;; ++it) {
-                int64_t rbu; int t0, t1;
-                if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+                int64_t rbu; int t0, t1, o;
+                {
+                    const int64_t seq = it;
+                    if (feed.dyn && leader) {
+                        // claim and publish up to one item ahead of the one about to be loaded
+                        while (!ended && seq_pub <= seq + 1) {
+                            const uint32_t c = atomicAdd_system(prm.work_counter, 1u);
+                            const uint32_t slot = (uint32_t)(seq_pub & 7);
+                            st_shared_u32(wslot0 + 4u * slot, c);
+                            st_shared_remote_u32(wslot0 + 4u * slot, 1u, c);
+                            mbar_arrive(wfull0 + 8u * slot);
+                            mbar_arrive_remote<false>(wfull0 + 8u * slot, 1u);
+                            ++seq_pub;
+                            ended = (long long)c >= prm.n_items;
+                        }
+                    }
+                    w = feed.get(seq);
+                }
+                if (!next_work<PAIR, SYM>(prm, w, rbu, t0, t1, o)) break;
                 if (t0 >= t1) continue;
                 const int64_t rb = prm.rb_begin + CPC * rbu + cta_rank;
                 // PAIR: both CTAs load; every complete_tx lands on the LEADER's barrier, which expects both halves
@@ -183,7 +232,8 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     a_ph ^= 1u;
                 }
-                for (int t = t0; t < t1; ++t) {
+                for (int i = 0; i < t1 - t0; ++i) {
+                    const int t = t0 + ((o + i >= t1 - t0) ? o + i - (t1 - t0) : o + i);     // start at offset o, wrap
                     for (int kb = 0; kb < prm.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1u);
                         if (leader) mbar_expect_tx(full_bar(s), (uint32_t)kStageBytes * CPC);
@@ -220,12 +270,18 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0 && leader) {
             int s = 0, as = 0;
             uint32_t ph = 0, a_ph = 0, acc_ph = 0;
+            int64_t w = 0;
+            unsigned long long n_done = 0;
             for (int64_t it = 0;; ++it) {
-                int64_t rbu; int t0, t1;
-                if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+                int64_t rbu; int t0, t1, o;
+                w = feed.get(it);
+                if (!next_work<PAIR, SYM>(prm, w, rbu, t0, t1, o)) break;
                 if (t0 >= t1) continue;
+                n_done += (unsigned long long)(t1 - t0);
                 if (A_RESIDENT) { mbar_wait(a_full, a_ph); a_ph ^= 1u; }
-                for (int t = t0; t < t1; ++t) {
+                for (int i = 0; i < t1 - t0; ++i) {
+                    const int t = t0 + ((o + i >= t1 - t0) ? o + i - (t1 - t0) : o + i);
+                    (void)t;
                     mbar_wait(tempty_bar(as), acc_ph ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
@@ -264,6 +320,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 // A block may be overwritten for the next item
                 if (A_RESIDENT) { if (PAIR) tc_commit_pair(a_empty); else tc_commit(a_empty); }
             }
+            if (prm.tiles_done && n_done) atomicAdd(prm.tiles_done, n_done);
         }
         __syncwarp();
     } else {
@@ -273,9 +330,11 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int kSliceCols = BN / kSlices;
         int as = 0;
         uint32_t acc_ph = 0;
+        int64_t w = 0;
         for (int64_t it = 0;; ++it) {
-            int64_t rbu; int t0, t1;
-            if (!next_work<PAIR, SYM>(prm, it, unit0, unit_stride, rbu, t0, t1)) break;
+            int64_t rbu; int t0, t1, o;
+            w = feed.get(it);
+            if (!next_work<PAIR, SYM>(prm, w, rbu, t0, t1, o)) break;
             if (t0 >= t1) continue;
             const int64_t rb = prm.rb_begin + CPC * rbu + cta_rank;
             const int64_t rowbase = rb * BM + q * 32;
@@ -283,7 +342,8 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int row_cell = SYM ? __ldg(prm.chunk_cell + (rowbase >> 5)) : 0;   // the cell of this warp's 32 rows
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             int cur_cell = -1;
-            for (int t = t0; t < t1; ++t) {
+            for (int i = 0; i < t1 - t0; ++i) {
+                const int t = t0 + ((o + i >= t1 - t0) ? o + i - (t1 - t0) : o + i);
                 // the four cell ids of this warp's half tile, requested before the accumulator wait
 #if VTF_CELL_PREFETCH
                 int cells[kChunksPerWarp];
@@ -390,7 +450,7 @@ template <bool A_RES, int STAGES, bool PAIR, bool SYM>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& maa, const CUtensorMap& mab,
                   const Params& prm, int grid, void* stream) {
     const size_t stage = kBBlockBytes / (PAIR ? 2 : 1) + (A_RES ? 0 : kABlockBytes);
-    const size_t smem = 1024 + (A_RES ? (size_t)prm.n_kb * kABlockBytes : 0) + STAGES * stage + 256;
+    const size_t smem = 1024 + (A_RES ? (size_t)prm.n_kb * kABlockBytes : 0) + STAGES * stage + 384;
     auto kern = sil_sweep_kernel<A_RES, STAGES, PAIR, SYM>;
     VTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "vtf_sil_sweep/smem");
     cudaLaunchConfig_t cfg = {};
@@ -451,6 +511,7 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
     prm.n_seg = (prm.n_tiles + prm.tiles_per_seg - 1) / prm.tiles_per_seg;
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = 0; prm.sym_world = 1;
+    prm.work_counter = nullptr; prm.n_items = 0; prm.tiles_done = nullptr; prm.chunk_tiles = 0;
     const int64_t n_units = units * prm.n_seg;
     if (pair) {
         const int grid = 2 * (int)min(slots, n_units);
@@ -467,8 +528,11 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
 // traffic); every off-diagonal 32 x 32 block also feeds the row sums of its COLUMNS through a warp
 // transpose-reduce.  Each rank sweeps unit pairs (q, U-1-q), q = rank, rank + world, ...; its cellsum then holds
 // partial sums for ALL rows and the caller adds the ranks' arrays (all-reduce) before the finish pass.
+// With `work_counter` (zero before the first rank starts; shared by all ranks, see vtf_shared_alloc) the unit pairs are
+// not dealt out by rank: every CTA pair of every rank claims the next sub-range from the counter.
 extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int d, float scale, const int32_t* chunk_cell,
-                                 int n_cells, int rank, int world, float* cellsum, void* stream) {
+                                 int n_cells, int rank, int world, float* cellsum, uint32_t* work_counter,
+                                 uint64_t* tiles_done, void* stream) {
     VTF_REQUIRE(Xh && aug && chunk_cell && cellsum && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0 &&
                     n_cells > 0 && world > 0 && rank >= 0 && rank < world && scale > 0.f,
                 "vtf_sil_sweep_sym (P % 256 == 0, d % 64 == 0, 64 <= d <= 1024)");
@@ -489,16 +553,26 @@ extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int
     prm.tiles_per_seg = prm.n_tiles;
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = rank; prm.sym_world = world;
-    const int64_t U = prm.n_rb / 2, n_q = (U + 1) / 2;
-    if (rank >= n_q) return VTF_OK;
-    const int64_t mine = (n_q - rank + world - 1) / world;
-    // cut every unit pair into sub-ranges until there are >= 12 work items per CTA pair (tail effect <= ~8%),
-    // but keep at least 8 tiles per sub-range so the resident A block is amortised
+    prm.work_counter = work_counter; prm.n_items = 0; prm.tiles_done = (unsigned long long*)tiles_done;
+    const int64_t U = prm.n_rb / 2;
+    // column chunk: <= 32 MB of B operand (a quarter of the 126 MB L2, so the chunk being left and the one being
+    // entered both stay resident), 16..256 tiles; VTF_SWEEP_CHUNK overrides.  Same-box A/B at 1M x 512 (static /
+    // claimed): 32 tiles 426 / 422 ms, 64 tiles 418 / 414 ms, 128 tiles 415 / 409 ms.
+    static int forced_chunk = -1;
+    if (forced_chunk < 0) { const char* e = getenv("VTF_SWEEP_CHUNK"); forced_chunk = e ? atoi(e) : 0; }
+    int64_t TC = (32ll << 20) / (256ll * d * 2);
+    TC = max((int64_t)16, min((int64_t)256, TC));
+    if (forced_chunk > 0) TC = forced_chunk;
+    TC = min(TC, U);
+    prm.chunk_tiles = (int)TC;
+    prm.n_seg = 1;
+    const int64_t nc_full = U / TC;
+    prm.n_items = TC * nc_full * (nc_full + 1) / 2 + (U % TC ? U : 0);
     const int64_t slots = num_sms() / 2;
-    int n_seg = 1;
-    while (mine * n_seg < 12 * slots && (U + 1) / (2 * n_seg) >= 8) n_seg *= 2;
-    prm.n_seg = n_seg;
-    const int grid = 2 * (int)min(slots, mine * n_seg);
+    if (work_counter) { prm.sym_rank = 0; prm.sym_world = 1; }        // claimed, not dealt out
+    const int64_t mine = work_counter ? prm.n_items : (prm.n_items - rank + world - 1) / world;
+    if (mine <= 0) return VTF_OK;
+    const int grid = 2 * (int)min(slots, mine);
     if (d <= 512) return tc::launch<true, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
     return tc::launch<false, 6, true, true>(ma, mb, maa, mab, prm, grid, stream);
 }

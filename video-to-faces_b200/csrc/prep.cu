@@ -4,6 +4,7 @@
 //   gather_rows     <- np.delete (dupes.py:68)
 // All HBM-bound: algorithmic bytes are N*d*4 read (+ N*d*4 written where a copy is produced).
 #include "common.cuh"
+#include <string.h>
 
 namespace vtf {
 
@@ -221,3 +222,44 @@ int vtf_gather_rows(const float* X, int d, const int64_t* idx, int64_t n_out, fl
 }
 
 }  // extern "C"
+
+// ---- device memory shared between ranks (CUDA IPC) ------------------------------------------------------------
+extern "C" int vtf_shared_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+    VTF_REQUIRE(bytes > 0 && ptr && handle, "vtf_shared_alloc");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void* p = nullptr;
+    VTF_CUDA(cudaMalloc(&p, bytes), "vtf_shared_alloc/cudaMalloc");
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(VTF_ERR_CUDA, "vtf_shared_alloc", cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *ptr = p;
+    return VTF_OK;
+}
+
+extern "C" int vtf_shared_open(const unsigned char handle[64], void** ptr) {
+    VTF_REQUIRE(handle && ptr, "vtf_shared_open");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    VTF_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "vtf_shared_open");
+    return VTF_OK;
+}
+
+extern "C" int vtf_shared_zero(void* ptr, size_t bytes, void* stream) {
+    VTF_REQUIRE(ptr && bytes > 0, "vtf_shared_zero");
+    VTF_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream), "vtf_shared_zero");
+    return VTF_OK;
+}
+
+extern "C" int vtf_shared_close(void* ptr) {
+    VTF_REQUIRE(ptr, "vtf_shared_close");
+    VTF_CUDA(cudaIpcCloseMemHandle(ptr), "vtf_shared_close");
+    return VTF_OK;
+}
+
+extern "C" int vtf_shared_free(void* ptr) {
+    VTF_REQUIRE(ptr, "vtf_shared_free");
+    VTF_CUDA(cudaFree(ptr), "vtf_shared_free");
+    return VTF_OK;
+}

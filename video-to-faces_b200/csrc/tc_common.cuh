@@ -96,6 +96,37 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
             ::"r"(bar), "r"(cta) : "memory");
     }
 }
+// wait with acquire at CLUSTER scope: the data guarded by the barrier was written by the other CTA of the pair
+// through distributed shared memory (st.shared::cluster + mbarrier.arrive.release.cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const unsigned long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+        if (done) return;
+        if (clock64() - t0 > kTimeoutCycles) __trap();
+    }
+}
+// store a word at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void st_shared_remote_u32(uint32_t addr, uint32_t cta, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}"
+        ::"r"(addr), "r"(cta), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // cute::Sm100MmaPeerBitMask: address of the same barrier in the even CTA
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
     asm volatile(

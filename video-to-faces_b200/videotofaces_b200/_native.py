@@ -51,7 +51,12 @@ SIGNATURES = {
     'vtf_sil_pack': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'vtf_absmax': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_sil_sweep': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
-    'vtf_sil_sweep_sym': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    'vtf_sil_sweep_sym': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_shared_alloc': (c_int, [c_sz, c_vp, c_vp]),
+    'vtf_shared_open': (c_int, [c_vp, c_vp]),
+    'vtf_shared_zero': (c_int, [c_vp, c_sz, c_vp]),
+    'vtf_shared_close': (c_int, [c_vp]),
+    'vtf_shared_free': (c_int, [c_vp]),
     'vtf_sil_finish_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     'vtf_sil_finish_cells': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
 }

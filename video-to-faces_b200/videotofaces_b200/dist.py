@@ -32,6 +32,12 @@ class Comm:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def broadcast_object(self, box, src=0):
+        """`box` is a one-element list; afterwards every rank holds rank `src`'s element (pickled, tiny)."""
+        if self.active:
+            self._dist.broadcast_object_list(box, src=src, group=self.group)
+        return box
+
     def allreduce_min(self, t):
         if self.active:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)

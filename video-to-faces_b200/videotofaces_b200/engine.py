@@ -12,6 +12,7 @@ Only O(k), O(d) and O(trials) scalars ever come back to the host inside these lo
 flags, candidate potentials, RNG draws); all O(N) work is in the kernels of csrc/.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -80,6 +81,11 @@ class GroupingEngine:
         self.events = []
         self.lockstep = True     # all fits of a k-range share each pass over X (False: one Lloyd loop per k)
         self.sym = None          # None: symmetric silhouette sweep for large inputs; True / False forces it
+        # symmetric sweep: claim work items from a counter shared by all ranks (NVLink peer memory) instead of dealing
+        # them out by rank -- a slower GPU then takes fewer items.  VTF_SWEEP_DYNAMIC=0 keeps the static split.
+        self.dynamic = os.environ.get('VTF_SWEEP_DYNAMIC', '1') != '0'
+        self._wc = None          # (device address of 2 uint32 counters on rank 0, keep-alive object), False = unavailable
+        self._wc_calls = 0
 
     def span(self, name, flops=0.0):
         return _Span(self, name, flops)
@@ -579,6 +585,49 @@ class GroupingEngine:
         c2c = torch.stack([lab[rep].to(torch.int32) for lab in labels_list]).contiguous()
         return perm, chunk_cell, c2c, G, P
 
+    def _work_counter(self):
+        """Device address of the zeroed work counter for the next symmetric sweep, or None (static schedule).
+        Two counters alternate: rank 0 zeroes the one for the NEXT sweep right before it launches this one -- every rank's
+        previous use of it ended before the all-reduce that closed that sweep completed anywhere, so the memset cannot
+        race with a claim.  Every rank must call this the same number of times (it does: once per sweep)."""
+        K, comm = self.K, self.comm
+        if not self.dynamic or not getattr(K, 'dynamic_schedule', False):
+            return None
+        if self._wc is None:
+            try:
+                if comm.active:
+                    ok, addr = 1, 0
+                    box = [None]
+                    if comm.rank == 0:
+                        try:
+                            addr, box[0] = K.shared_alloc(64)
+                        except Exception:  # noqa: BLE001
+                            box[0] = None
+                    comm.broadcast_object(box, src=0)
+                    if box[0] is None:
+                        ok = 0
+                    elif comm.rank != 0:
+                        try:
+                            addr = K.shared_open(box[0])
+                        except Exception:  # noqa: BLE001
+                            ok = 0
+                    flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                    comm.allreduce_min(flag)                       # all ranks or none
+                    self._wc = (addr, None) if int(flag.item()) == 1 else False
+                else:
+                    t = K.zeros((16,), torch.int32)
+                    self._wc = (t.data_ptr(), t)
+            except Exception:  # noqa: BLE001
+                self._wc = False
+        if self._wc is False:
+            return None
+        base = self._wc[0]
+        n = self._wc_calls
+        self._wc_calls += 1
+        if comm.rank == 0:
+            K.shared_zero(base + 4 * ((n + 1) % 2), 4)
+        return base + 4 * (n % 2)
+
     def sil_scale(self, Xc):
         """Power-of-two scale s for the fp16 operand and the split of the half squared norms m = s^2 |x|^2 / 2
         that ride in the MMA as fp16 pieces m * 2^-shift against the constant 2^shift.
@@ -613,11 +662,11 @@ class GroupingEngine:
         sym = (U >= TC_SYM_MIN_UNITS * comm.world) if self.sym is None else bool(self.sym)
         if sym:
             # D is symmetric: sweep the tiles on or above the diagonal only; executed MMA flops = d * P^2 * (1 + 1/U)
-            n_q = (U + 1) // 2
-            mine = len(range(comm.rank, n_q, comm.world))
-            tiles = sum((U - q) + (q + 1 if U - 1 - q != q else 0) for q in range(comm.rank, n_q, comm.world))
-            with self.span('sil_sweep', flops=2.0 * tiles * 256 * 256 * Xc.shape[1]):
-                K.sil_sweep_sym(Xh, aug, scale, chunk_cell, G, comm.rank, comm.world, cellsum)
+            counter = self._work_counter()
+            tiles_done = K.zeros((1,), torch.int64)
+            per_tile = 2.0 * 256 * 256 * Xc.shape[1]
+            with self.span('sil_sweep', flops=lambda: per_tile * float(tiles_done.item())):
+                K.sil_sweep_sym(Xh, aug, scale, chunk_cell, G, comm.rank, comm.world, cellsum, counter, tiles_done)
             with self.span('sil_allreduce'):
                 comm.allreduce_sum(cellsum)
         else:

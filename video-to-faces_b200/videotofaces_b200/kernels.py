@@ -262,10 +262,34 @@ class CudaKernels:
         nv.call('vtf_sil_sweep', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
                 c_i64(rb_begin), c_i64(rb_end), ptr(cellsum), stream())
 
-    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum):
+    def sil_sweep_sym(self, Xh, aug, scale, chunk_cell, n_cells, rank, world, cellsum, counter=None, tiles_done=None):
+        """`counter`: device address (int) of the zeroed uint32 work counter shared by all ranks -> dynamic schedule;
+        None -> static round-robin by rank.  `tiles_done`: int64 [1] tensor, += tiles computed by this launch."""
         P, d = Xh.shape
         nv.call('vtf_sil_sweep_sym', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(scale), ptr(chunk_cell), c_int(n_cells),
-                c_int(rank), c_int(world), ptr(cellsum), stream())
+                c_int(rank), c_int(world), ptr(cellsum), None if counter is None else nv.c_vp(counter), ptr(tiles_done),
+                stream())
+
+    # ------------------------------------------------------------------ memory shared between ranks (CUDA IPC)
+    dynamic_schedule = True            # the sweep can claim work items from a shared counter
+
+    def shared_alloc(self, nbytes):
+        """(device address, 64-byte handle) of a zeroed allocation other ranks can map."""
+        import ctypes
+        p = nv.c_vp()
+        h = (ctypes.c_ubyte * 64)()
+        nv.call('vtf_shared_alloc', nv.c_sz(nbytes), ctypes.byref(p), h)
+        return int(p.value), bytes(h)
+
+    def shared_open(self, handle):
+        import ctypes
+        p = nv.c_vp()
+        h = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        nv.call('vtf_shared_open', h, ctypes.byref(p))
+        return int(p.value)
+
+    def shared_zero(self, addr, nbytes):
+        nv.call('vtf_shared_zero', nv.c_vp(addr), nv.c_sz(nbytes), stream())
 
     def sil_finish_cells(self, cellsum, cell_to_cluster, k, perm, labels, counts, p_begin, p_end, out_slot):
         n_cells, P = cellsum.shape
