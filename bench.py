@@ -143,11 +143,31 @@ def run_reference(args):
                             rows=args.cpu_rows, dim=args.dim, ks=KS),
                 cpu_baseline=dict(value=value, unit='embeddings/s', cores=info['cores'], kind='port', sample=sample, info=info),
                 e2e=dict(value=value, unit='embeddings/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner from C at
+    any NCCL_DEBUG level >= VERSION, which includes WARN), so file descriptor 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -158,8 +178,6 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line the driver reads
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import __graft_entry__ as ge
     ge.build()
@@ -276,7 +294,7 @@ def main():
                     clocks=sampler.summary(), gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu,
                     phases_ms=phases, n_iter=[r.n_iter for r in res], scores=[list(s) for s in scores],
                     best_k=max(scores, key=lambda s: s[1])[0])
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
