@@ -39,6 +39,9 @@ namespace tc {
 #ifndef VTF_EPI_WARPS
 #define VTF_EPI_WARPS 8    // same-box A/B: 8 beats 16 in both forms (full 736 vs 772 ms, symmetric 407 vs 424 ms)
 #endif
+#ifndef VTF_EPI_FRAG
+#define VTF_EPI_FRAG 1     // symmetric sweep: read TMEM in the 16x256b fragment layout (7 instead of 31 shuffles per block)
+#endif
 constexpr int kEpiWarps = VTF_EPI_WARPS;                 // 8 or 16: warps that drain TMEM (4 lane quarters x column slices)
 constexpr int kSlices = kEpiWarps / 4;                   // column slices of the 256-wide tile
 constexpr int kChunksPerWarp = (BN / 32) / kSlices;      // 32-column chunks per warp per tile
@@ -328,6 +331,8 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int q = warp & 3;                 // TMEM lane quarter this warp can read
         const int slice = (warp - 2) >> 2;      // which column slice of the 256-wide tile
         constexpr int kSliceCols = BN / kSlices;
+        constexpr bool FRAG = SYM && (VTF_EPI_FRAG != 0);
+        const int g = lane >> 2, tq = lane & 3;
         int as = 0;
         uint32_t acc_ph = 0;
         int64_t w = 0;
@@ -342,6 +347,21 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int row_cell = SYM ? __ldg(prm.chunk_cell + (rowbase >> 5)) : 0;   // the cell of this warp's 32 rows
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             int cur_cell = -1;
+            // row sums of the finished cell run -> cellsum (warp-uniform call).  One row per thread in the 32x32b layout;
+            // in the fragment layout the four threads of a group first add their column partials (2 shuffles per
+            // accumulator) and thread tq then owns row g + 8 tq.
+            auto flush_rows = [&](int cell_id) {
+                if (FRAG) {
+                    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+                    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+                    acc3 += __shfl_xor_sync(0xffffffffu, acc3, 1); acc3 += __shfl_xor_sync(0xffffffffu, acc3, 2);
+                    const float mine = tq == 0 ? acc0 : tq == 1 ? acc1 : tq == 2 ? acc2 : acc3;
+                    atomicAdd(prm.cellsum + (size_t)cell_id * prm.P + rowbase + g + 8 * tq, mine * prm.flush_scale);
+                } else {
+                    atomicAdd(prm.cellsum + (size_t)cell_id * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);
+                }
+            };
             for (int i = 0; i < t1 - t0; ++i) {
                 const int t = t0 + ((o + i >= t1 - t0) ? o + i - (t1 - t0) : o + i);
                 // the four cell ids of this warp's half tile, requested before the accumulator wait
@@ -365,15 +385,19 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int64_t col0 = (int64_t)t * BN + slice * kSliceCols + c * 32;
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (uint32_t)(as * BN + slice * kSliceCols + c * 32) + ((uint32_t)(q * 32) << 16);
-                    VTF_TMEM_LD32(taddr, v);
+                    if (FRAG) {
+                        VTF_TMEM_LD16X256(taddr, v, 0);                       // rows  0..15 of this warp's 32
+                        VTF_TMEM_LD16X256(taddr + (16u << 16), v, 16);        // rows 16..31
+                    } else {
+                        VTF_TMEM_LD32(taddr, v);
+                    }
 #if VTF_CELL_PREFETCH
                     const int cell = cells[c];
 #else
                     const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
 #endif
                     if (cell != cur_cell) {
-                        if (cur_cell >= 0)
-                            atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);
+                        if (cur_cell >= 0) flush_rows(cur_cell);
                         acc0 = acc1 = acc2 = acc3 = 0.f;
                         cur_cell = cell;
                     }
@@ -383,29 +407,72 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     float r[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
-                    if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
+                    if (FRAG) {
+                        // register j: row 16 (j / 16) + 8 ((j / 2) % 2) + g, column 8 ((j % 16) / 4) + 2 tq + j % 2
+                        if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = (j == lane) ? 0.f : r[j];
-                    }
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        acc0 += r[4 * j4 + 0]; acc1 += r[4 * j4 + 1]; acc2 += r[4 * j4 + 2]; acc3 += r[4 * j4 + 3];
-                    }
-                    if (SYM && t != (int)rbu) {
-                        // D_qp = D_pq: the same 32 x 32 block, summed over this warp's rows (all in cell row_cell), is
-                        // the contribution to the row sums of columns col0..col0+31.  Transpose-reduce: after the five
-                        // exchange steps lane l holds the column sum of column col0 + l.
-#pragma unroll
-                        for (int o = 16; o >= 1; o >>= 1) {
-                            const bool up = (lane & o) != 0;
-#pragma unroll
-                            for (int j = 0; j < o; ++j) {
-                                const float keep = up ? r[j + o] : r[j];
-                                const float send = up ? r[j] : r[j + o];
-                                r[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            for (int j = 0; j < 32; ++j) {
+                                const int row = 16 * (j >> 4) + 8 * ((j >> 1) & 1) + g, col = 8 * ((j & 15) >> 2) + 2 * tq + (j & 1);
+                                r[j] = (row == col) ? 0.f : r[j];
                             }
                         }
-                        atomicAdd(prm.cellsum + (size_t)row_cell * prm.P + col0 + lane, r[0] * prm.flush_scale);
+                        // row sums: acc0..3 = rows g, g + 8, g + 16, g + 24 (this thread's 8 columns; the other three
+                        // threads of the group hold the rest -- combined at flush time only)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc0 += r[4 * i + 0] + r[4 * i + 1];
+                            acc1 += r[4 * i + 2] + r[4 * i + 3];
+                            acc2 += r[16 + 4 * i + 0] + r[16 + 4 * i + 1];
+                            acc3 += r[16 + 4 * i + 2] + r[16 + 4 * i + 3];
+                        }
+                        if (t != (int)rbu) {
+                            // D_qp = D_pq: the block summed over this warp's 32 rows (all in cell row_cell) is the contribution
+                            // to the row sums of columns col0..col0+31.  Four rows are added inside the thread; the eight
+                            // threads that share tq then transpose-reduce their 8 column partials in 4 + 2 + 1 shuffles, after
+                            // which the thread holds column 8 (g / 2) + 2 tq + g % 2.
+                            float cs[8];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                cs[2 * i + 0] = (r[4 * i + 0] + r[4 * i + 2]) + (r[16 + 4 * i + 0] + r[16 + 4 * i + 2]);
+                                cs[2 * i + 1] = (r[4 * i + 1] + r[4 * i + 3]) + (r[16 + 4 * i + 1] + r[16 + 4 * i + 3]);
+                            }
+#pragma unroll
+                            for (int o = 4; o >= 1; o >>= 1) {                 // lane bit 4 o: 16, 8, 4
+                                const bool up = (lane & (4 * o)) != 0;
+#pragma unroll
+                                for (int j = 0; j < o; ++j) {
+                                    const float keep = up ? cs[j + o] : cs[j];
+                                    const float send = up ? cs[j] : cs[j + o];
+                                    cs[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * o);
+                                }
+                            }
+                            atomicAdd(prm.cellsum + (size_t)row_cell * prm.P + col0 + 8 * (g >> 1) + 2 * tq + (g & 1),
+                                      cs[0] * prm.flush_scale);
+                        }
+                    } else {
+                        if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = (j == lane) ? 0.f : r[j];
+                        }
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            acc0 += r[4 * j4 + 0]; acc1 += r[4 * j4 + 1]; acc2 += r[4 * j4 + 2]; acc3 += r[4 * j4 + 3];
+                        }
+                        if (SYM && t != (int)rbu) {
+                            // one TMEM lane = one row per thread: transpose-reduce over all 32 lanes, 16 + 8 + 4 + 2 + 1 shuffles;
+                            // afterwards lane l holds the column sum of column col0 + l
+#pragma unroll
+                            for (int o = 16; o >= 1; o >>= 1) {
+                                const bool up = (lane & o) != 0;
+#pragma unroll
+                                for (int j = 0; j < o; ++j) {
+                                    const float keep = up ? r[j + o] : r[j];
+                                    const float send = up ? r[j] : r[j + o];
+                                    r[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                                }
+                            }
+                            atomicAdd(prm.cellsum + (size_t)row_cell * prm.P + col0 + lane, r[0] * prm.flush_scale);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -413,8 +480,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (lane == 0) { if (PAIR) mbar_arrive_remote<SYM>(tempty_bar(as), 0u); else mbar_arrive(tempty_bar(as)); }
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
-            if (cur_cell >= 0)
-                atomicAdd(prm.cellsum + (size_t)cur_cell * prm.P + p, ((acc0 + acc1) + (acc2 + acc3)) * prm.flush_scale);
+            if (cur_cell >= 0) flush_rows(cur_cell);
         }
     }
 

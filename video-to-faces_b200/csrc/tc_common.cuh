@@ -189,6 +189,18 @@ constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint
           "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
         : "r"(taddr))
 
+// 16 lanes x 256 bits, 4 repetitions = 16 lanes x 32 columns in the mma.m16n8 accumulator layout: thread (g = lane / 4,
+// tq = lane % 4) receives, for column group i = 0..3, v[4i + {0,1}] = row g, columns 8i + 2tq + {0,1} and
+// v[4i + {2,3}] = row g + 8, same columns (verified on the device by tools/probe/tmem_ld_layout.cu).
+#define VTF_TMEM_LD16X256(taddr, v, o)                                                                       \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "                                                            \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                    \
+        : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),     \
+          "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),  \
+          "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                  \
+        : "r"(taddr))
+
 // the "+r" operands tie every later use of v[] to the completion of the load
 #define VTF_TMEM_WAIT(v)                                                                                     \
     asm volatile("tcgen05.wait::ld.sync.aligned;"                                                            \
