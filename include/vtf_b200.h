@@ -184,8 +184,9 @@ int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* strea
  * augmented operand aug = [A flavour | B flavour], each P*16 fp16 in UMMA no-swizzle K-major tile order:
  * three fp16 pieces of m_p * 2^-shift (m_p = |Xh[p,:]|^2 / 2 from the ROUNDED values, so the distance is
  * the exact distance between the rounded points) against the constant 2^shift, so that ONE extra K=16 MMA
- * adds -m_p - m_q to the Gram accumulator.  Padding rows get m = -pad_m (pad_m >= 4 * max m), which clamps
- * every distance to them to 0.  half_sqn[P] (nullable) receives m.  P % 256 == 0, d % 64 == 0.      */
+ * adds -m_p - m_q to the Gram accumulator.  Padding rows get an all-zero augmented block, so every accumulator
+ * entry that involves one is exactly 0 (distance 0); pad_m (>= 4 * max m) only bounds the shift.  half_sqn[P]
+ * (nullable) receives m (-pad_m for padding rows).  P % 256 == 0, d % 64 == 0.                       */
 int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale,
                  int shift, float pad_m, void* Xh, void* aug, float* half_sqn, void* stream);
 /* out[0] = max |x| (picks the power-of-two fp16 scale).                                     */

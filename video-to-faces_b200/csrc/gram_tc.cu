@@ -346,12 +346,14 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int64_t p = rowbase + lane;
             const int row_cell = SYM ? __ldg(prm.chunk_cell + (rowbase >> 5)) : 0;   // the cell of this warp's 32 rows
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            float2 fa0 = make_float2(0.f, 0.f), fa1 = fa0, fa2 = fa0, fa3 = fa0;      // fragment layout: (even, odd) columns
             int cur_cell = -1;
             // row sums of the finished cell run -> cellsum (warp-uniform call).  One row per thread in the 32x32b layout;
             // in the fragment layout the four threads of a group first add their column partials (2 shuffles per
             // accumulator) and thread tq then owns row g + 8 tq.
             auto flush_rows = [&](int cell_id) {
                 if (FRAG) {
+                    acc0 = fa0.x + fa0.y; acc1 = fa1.x + fa1.y; acc2 = fa2.x + fa2.y; acc3 = fa3.x + fa3.y;
                     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
                     acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
                     acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
@@ -399,15 +401,19 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (cell != cur_cell) {
                         if (cur_cell >= 0) flush_rows(cur_cell);
                         acc0 = acc1 = acc2 = acc3 = 0.f;
+                        fa0 = fa1 = fa2 = fa3 = make_float2(0.f, 0.f);
                         cur_cell = cell;
                     }
                     VTF_TMEM_WAIT(v);
                     // the accumulator holds T = s^2 (x_p.x_q - |x_p|^2/2 - |x_q|^2/2) = -s^2 D^2 / 2:
                     // distance = sqrt(max(-T, 0)) * sqrt(2)/s, the constant factor applied once per flush
                     float r[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
                     if (FRAG) {
+                        // |T| instead of max(-T, 0): the two differ only where rounding noise made the squared distance of
+                        // (nearly) coincident rows negative, where either answer is noise of the same size -- and the
+                        // absolute value rides on the MUFU operand for free (one FMNMX less per element)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fabsf(__uint_as_float(v[j])));
                         // register j: row 16 (j / 16) + 8 ((j / 2) % 2) + g, column 8 ((j % 16) / 4) + 2 tq + j % 2
                         if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
 #pragma unroll
@@ -416,14 +422,14 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 r[j] = (row == col) ? 0.f : r[j];
                             }
                         }
-                        // row sums: acc0..3 = rows g, g + 8, g + 16, g + 24 (this thread's 8 columns; the other three
-                        // threads of the group hold the rest -- combined at flush time only)
+                        // row sums, two columns at a time (packed fp32x2 adds): fa0..3 = rows g, g + 8, g + 16, g + 24 (this
+                        // thread's 8 columns; the other three threads of the group hold the rest -- combined at flush time)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            acc0 += r[4 * i + 0] + r[4 * i + 1];
-                            acc1 += r[4 * i + 2] + r[4 * i + 3];
-                            acc2 += r[16 + 4 * i + 0] + r[16 + 4 * i + 1];
-                            acc3 += r[16 + 4 * i + 2] + r[16 + 4 * i + 3];
+                            fa0 = __fadd2_rn(fa0, make_float2(r[4 * i + 0], r[4 * i + 1]));
+                            fa1 = __fadd2_rn(fa1, make_float2(r[4 * i + 2], r[4 * i + 3]));
+                            fa2 = __fadd2_rn(fa2, make_float2(r[16 + 4 * i + 0], r[16 + 4 * i + 1]));
+                            fa3 = __fadd2_rn(fa3, make_float2(r[16 + 4 * i + 2], r[16 + 4 * i + 3]));
                         }
                         if (t != (int)rbu) {
                             // D_qp = D_pq: the block summed over this warp's 32 rows (all in cell row_cell) is the contribution
@@ -433,8 +439,11 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             float cs[8];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                cs[2 * i + 0] = (r[4 * i + 0] + r[4 * i + 2]) + (r[16 + 4 * i + 0] + r[16 + 4 * i + 2]);
-                                cs[2 * i + 1] = (r[4 * i + 1] + r[4 * i + 3]) + (r[16 + 4 * i + 1] + r[16 + 4 * i + 3]);
+                                const float2 c2 = __fadd2_rn(
+                                    __fadd2_rn(make_float2(r[4 * i + 0], r[4 * i + 1]), make_float2(r[4 * i + 2], r[4 * i + 3])),
+                                    __fadd2_rn(make_float2(r[16 + 4 * i + 0], r[16 + 4 * i + 1]), make_float2(r[16 + 4 * i + 2], r[16 + 4 * i + 3])));
+                                cs[2 * i + 0] = c2.x;
+                                cs[2 * i + 1] = c2.y;
                             }
 #pragma unroll
                             for (int o = 4; o >= 1; o >>= 1) {                 // lane bit 4 o: 16, 8, 4
@@ -450,6 +459,8 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                       cs[0] * prm.flush_scale);
                         }
                     } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
                         if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
 #pragma unroll
                             for (int j = 0; j < 32; ++j) r[j] = (j == lane) ? 0.f : r[j];

@@ -32,7 +32,8 @@ __device__ __forceinline__ void store_aug(__half* augA, __half* augB, int64_t p,
 
 // warp per output row p: Xh[p,:] = fp16_rn(scale * X[perm[p],:]); m_p = |Xh[p,:]|^2 / 2 computed from the
 // ROUNDED values, so the distance is the exact distance between the rounded points.  Padding rows are zero
-// vectors with m = -pad_m (a large negative half-norm): every distance to them clamps to 0.
+// vectors with an ALL-ZERO augmented block (no norm pieces and no constant either): every product that involves a
+// padding row or column is exactly 0, so T = 0 and the distance is 0 without any clamp in the epilogue.
 __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__ X, int64_t N, int d,
                                                        const int64_t* __restrict__ perm, int64_t P, float scale,
                                                        float inv_pow, float cpow, float pad_m,
@@ -48,7 +49,11 @@ __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__
         if (src < 0) {
             for (int v = lane; v < nvec; v += 32) out[v] = make_uint2(0u, 0u);
             if (lane == 0) {
-                store_aug(augA, augB, p, -pad_m * inv_pow, cpow);
+                const size_t off = (size_t)(p >> 3) * 128 + (size_t)(p & 7) * 8;     // in halfs, as in store_aug
+                *reinterpret_cast<uint4*>(augA + off) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(augB + off) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(augA + off + 64) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(augB + off + 64) = make_uint4(0u, 0u, 0u, 0u);
                 if (half_sqn) half_sqn[p] = -pad_m;
             }
             continue;
