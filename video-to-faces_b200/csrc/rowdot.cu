@@ -207,6 +207,18 @@ static int launch_rowdot(const float* X, int64_t N, int d, const float* C, int k
     return VTF_OK;
 }
 
+// register-tiled fast path (rowtile.cu): 0 = launched, 1 = shape not covered, < 0 = error
+int rowtile_lloyd(const float* X, int64_t N, int d, const float* C_all, const Segs& sg, int32_t* labels,
+                  unsigned long long* counts, unsigned long long* n_changed, void* stream, const char* what);
+int rowtile_classify(const float* X, int64_t N, int d, const float* R, int nR, float thr, float* dist, int64_t* label,
+                     void* stream, const char* what);
+
+static bool use_rowtile() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VTF_ROWTILE"); v = (e && atoi(e) == 0) ? 0 : 1; }    // VTF_ROWTILE=0: rowdot only
+    return v == 1;
+}
+
 }  // namespace vtf
 
 using namespace vtf;
@@ -220,6 +232,10 @@ int vtf_lloyd_assign(const float* Xc, int64_t N, int d, const float* C, int k, i
     if (N == 0) return VTF_OK;
     LloydEpi le{labels, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(n_changed), {}};
     le.sg.n = 1; le.sg.off[0] = 0; le.sg.off[1] = k; le.sg.active = 1u; le.sg.label_stride = 0;
+    if (use_rowtile()) {
+        const int rc = rowtile_lloyd(Xc, N, d, C, le.sg, labels, le.counts, le.n_changed, stream, "vtf_lloyd_assign");
+        if (rc <= 0) return rc;
+    }
     ClassifyEpi ce{nullptr, nullptr, -1.f};
     return launch_rowdot<0>(Xc, N, d, C, k, le, ce, stream, "vtf_lloyd_assign");
 }
@@ -235,6 +251,27 @@ int vtf_lloyd_assign_multi(const float* Xc, int64_t N, int d, const float* C_all
     le.sg.n = n_lab; le.sg.active = active; le.sg.label_stride = label_stride;
     for (int i = 0; i <= n_lab; ++i) le.sg.off[i] = k_off_h[i];
     VTF_REQUIRE(k_off_h[0] == 0 && k_off_h[n_lab] > 0, "vtf_lloyd_assign_multi: k_off must start at 0");
+    if (use_rowtile()) {
+        // the register-tiled kernel takes up to 32 active centres per pass: hand it the active labellings in runs of
+        // sum(k) <= 32 (one pass over X each); whatever it cannot take (k > 32, odd d) stays with the warp-per-row kernel
+        uint32_t left = active, run = 0;
+        int run_k = 0;
+        for (int L = 0; L <= n_lab; ++L) {
+            const bool act = L < n_lab && ((active >> L) & 1u);
+            const int kL = act ? k_off_h[L + 1] - k_off_h[L] : 0;
+            if (run && (L == n_lab || (act && run_k + kL > 32))) {
+                Segs sub = le.sg;
+                sub.active = run;
+                const int rc = rowtile_lloyd(Xc, N, d, C_all, sub, labels, le.counts, le.n_changed, stream, "vtf_lloyd_assign_multi");
+                if (rc < 0) return rc;
+                if (rc == 0) left &= ~run;
+                run = 0; run_k = 0;
+            }
+            if (act && kL <= 32) { run |= 1u << L; run_k += kL; }
+        }
+        if (left == 0) return VTF_OK;
+        le.sg.active = left;
+    }
     ClassifyEpi ce{nullptr, nullptr, -1.f};
     return launch_rowdot<0>(Xc, N, d, C_all, k_off_h[n_lab], le, ce, stream, "vtf_lloyd_assign_multi");
 }
@@ -243,6 +280,10 @@ int vtf_cosine_classify(const float* Xn, int64_t N, int d, const float* Rn, int 
                         int64_t* label, void* stream) {
     VTF_REQUIRE(Xn && Rn && dist && label && N >= 0 && d > 0 && d % 4 == 0 && R > 0, "vtf_cosine_classify");
     if (N == 0) return VTF_OK;
+    if (use_rowtile()) {
+        const int rc = rowtile_classify(Xn, N, d, Rn, R, thr, dist, label, stream, "vtf_cosine_classify");
+        if (rc <= 0) return rc;
+    }
     LloydEpi le{nullptr, nullptr, nullptr, {}};
     ClassifyEpi ce{dist, label, thr};
     return launch_rowdot<1>(Xn, N, d, Rn, R, le, ce, stream, "vtf_cosine_classify");
