@@ -129,6 +129,54 @@ int vtf_lloyd_update_multi(const double* sums, const int64_t* counts, const int6
                            const int32_t* k_off_h, uint32_t active, int d, const float* C_old, float* C_new,
                            double* C64, double* stats, int stats_stride, void* stream);
 
+/* ---- a6, wide form: the E-step of a whole k-range as one contraction X.C^T on the tensor cores -----------------
+ * For k-ranges such as --clusters '2-32' (grouping.py:99-101 fits KMeans once per k; 527 centres in total) the
+ * E-step SGEMM of SK/cluster/_k_means_lloyd.pyx:196-218 is compute-bound: 2*N*sum(k)*d flop per lock-step
+ * iteration.  These entry points run it on tcgen05 and keep the M-step proportional to the rows that moved.
+ *
+ * pack_centres: the column operand of one launch.  Column c takes centre row col_src[c] of C_all (-1 = padding) and
+ * the info word col_info[c] = flags | local_index << 4 | labelling << 20 (flag 2 = last centre of its labelling);
+ * writes fp16 hi / lo pieces of scale * c [Kp, d], tab[c] = {|c|^2 / 2 (fp32, +inf for padding), info} and
+ * *cmax2h = bits of max |c|^2 / 2.  Kp % 256 == 0.  The row operand comes from vtf_dedup_pack (same split).
+ * assign: labels_new[L * label_stride + row] = argmin_c (|c|^2/2 - x.c) over the columns of labelling L, first
+ * index on ties; scores from three fp16 MMAs (hi.hi + hi.lo + lo.hi), fp32 accumulate in TMEM.  Every (row, L)
+ * with another centre within eps * |x_row| * max|c| of the best score is appended to fix[] as
+ * {row, L, mask lo, mask hi} (bit (index & 63) set for every candidate); *n_fix counts them (zeroed by the caller).
+ * refine: decides the listed (row, L) with exact fp32 dot products (the arithmetic of vtf_lloyd_assign), so the
+ * result equals the fp32 kernels'.  rown[P] = |x| per row (0 for padding).  Kp <= 2048 per launch.            */
+int vtf_wide_pack_centres(const float* C_all, int d, const int32_t* col_src, const uint32_t* col_info, int Kp,
+                          float scale, void* Bhi, void* Blo, float* tab, uint32_t* cmax2h, void* stream);
+int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P, int d, const void* Bhi,
+                    const void* Blo, int Kp, const float* tab, const float* rown, const uint32_t* cmax2h,
+                    float scale, float eps, int32_t* labels_new, int64_t label_stride, void* fix, uint32_t* n_fix,
+                    uint32_t fix_cap, void* stream);
+int vtf_wide_refine(const float* X, int d, const float* C_all, const float* tab, int n_lab, const int32_t* k_off_h,
+                    const int32_t* col0_h, const void* fix, const uint32_t* n_fix, uint32_t fix_cap,
+                    int32_t* labels_new, int64_t label_stride, void* stream);
+/* count: counts[k_off[L] + c] += rows of labelling L with new label c, changed[L] += rows whose new label differs
+ * from the old one (SK/cluster/_kmeans.py:723), for the active labellings.  commit: labels_old = labels_new and,
+ * for labellings with changed[L] <= cap, items[] += {row, L, old, new} (*n_items zeroed here).                 */
+int vtf_wide_count(const int32_t* lab_new, int64_t new_stride, const int32_t* lab_old, int64_t old_stride,
+                   int64_t n, int n_lab, const int32_t* k_off_h, uint32_t active, int64_t* counts,
+                   int64_t* changed, void* stream);
+int vtf_wide_commit(const int32_t* lab_new, int64_t new_stride, int32_t* lab_old, int64_t old_stride, int64_t n,
+                    int n_lab, const int32_t* k_off_h, uint32_t active, const int64_t* changed, int64_t cap,
+                    void* items, uint32_t* n_items, uint32_t items_cap, void* stream);
+/* M-step sums (SK/cluster/_k_means_lloyd.pyx:215-218) in 64-bit fixed point, acc[slot, j] = sum round(x_j * two_s):
+ * integer adds are exact and order-independent, so delta (+x to the new slot, -x from the old one, for the listed
+ * rows) and full (recompute the labellings of group [L0, L1) with changed[L] > cap from the labels) give
+ * bit-identical results, on one GPU or summed over ranks.  ws: vtf_wide_sums_ws_bytes(slots in the group, d);
+ * at most 100 slots per group.  update: vtf_lloyd_update_multi on acc / two_s, one CTA per labelling.          */
+int vtf_wide_sums_delta(const float* X, int d, const void* items, const uint32_t* n_items, uint32_t items_cap,
+                        int n_lab, const int32_t* k_off_h, double two_s, int64_t* acc, void* stream);
+size_t vtf_wide_sums_ws_bytes(int k_group, int d);
+int vtf_wide_sums_full(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
+                       const int32_t* k_off_h, uint32_t active, int L0, int L1, const int64_t* changed, int64_t cap,
+                       double two_s, int64_t* acc, void* ws, void* stream);
+int vtf_wide_update(const int64_t* acc, double inv_two_s, const int64_t* counts, const int64_t* changed, int n_lab,
+                    const int32_t* k_off_h, uint32_t active, int d, const float* C_old, float* C_new, double* stats,
+                    int stats_stride, void* stream);
+
 /* ---- a3: nearest-reference classification (grouping.py:51-56) -----------------------------
  * Xn, Rn are cosine-normalised.  dist[N,R] = clip(1 - Xn.Rn^T, 0, 2) (fp32, kept for the
  * '%.4f' log, grouping.py:63); label[i] = argmin (first index), or R when

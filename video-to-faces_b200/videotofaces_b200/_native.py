@@ -37,6 +37,19 @@ SIGNATURES = {
     'vtf_cluster_sums_multi': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     'vtf_cluster_dispersion_multi': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_lloyd_update_multi': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    'vtf_wide_pack_centres': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_wide_assign': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64,
+                                c_vp, c_vp, ctypes.c_uint32, c_vp]),
+    'vtf_wide_refine': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_i64, c_vp]),
+    'vtf_wide_count': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    'vtf_wide_commit': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_i64, c_vp, c_vp,
+                                ctypes.c_uint32, c_vp]),
+    'vtf_wide_sums_delta': (c_int, [c_vp, c_int, c_vp, c_vp, ctypes.c_uint32, c_int, c_vp, ctypes.c_double, c_vp, c_vp]),
+    'vtf_wide_sums_ws_bytes': (c_sz, [c_int, c_int]),
+    'vtf_wide_sums_full': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, c_int, c_int, c_vp, c_i64,
+                                   ctypes.c_double, c_vp, c_vp, c_vp]),
+    'vtf_wide_update': (c_int, [c_vp, ctypes.c_double, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_int,
+                                c_vp]),
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),

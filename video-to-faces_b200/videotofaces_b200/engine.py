@@ -23,6 +23,10 @@ TC_MIN_ROWS = 4096        # below this the exact fp32 silhouette kernel is used 
 TC_SYM_MIN_UNITS = 148    # symmetric (upper-triangle) sweep once there are at least 2 units of 256 rows per CTA pair
 TC_DEDUP_MIN_ROWS = 8192  # below this the fp32 FMA dedup kernel is used
 TC_MAX_CELLSUM_BYTES = 32 << 30
+WIDE_MIN_SUM_K = 33       # sum(k) of a k-range from which the E-step runs as one tensor-core contraction (lloyd_tc.cu);
+                          # below it a single register-tiled pass (rowtile.cu) is HBM-bound and cheaper
+WIDE_MIN_ROWS = 8192
+WIDE_MAX_COLS = 2048      # centre columns per launch (the kernel keeps their table in shared memory)
 
 
 class KMeansResult:
@@ -35,7 +39,7 @@ class KMeansResult:
 
 class FitContext:
     """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
-    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol')
+    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide')
 
 
 def n_local_trials(k):
@@ -81,6 +85,9 @@ class GroupingEngine:
         self.events = []
         self.lockstep = True     # all fits of a k-range share each pass over X (False: one Lloyd loop per k)
         self.sym = None          # None: symmetric silhouette sweep for large inputs; True / False forces it
+        self.wide = None         # None: tensor-core E-step for wide k-ranges on large inputs; True / False forces it
+        self.wide_eps_scale = float(os.environ.get('VTF_WIDE_EPS_SCALE', '1'))
+        self.wide_stats = {}     # iterations / fix-list and change-list sizes of the last wide run (tests, tools)
         # symmetric sweep: claim work items from a counter shared by all ranks (NVLink peer memory) instead of dealing
         # them out by rank -- a slower GPU then takes fewer items.  VTF_SWEEP_DYNAMIC=0 keeps the static split.
         self.dynamic = os.environ.get('VTF_SWEEP_DYNAMIC', '1') != '0'
@@ -339,6 +346,12 @@ class GroupingEngine:
         (each fit keeps its own stopping rule and freezes when it is done, so results equal the separate fits)."""
         out = [None] * len(C0_list)
         ks = [int(c.shape[0]) for c in C0_list]
+        if self._use_wide(ctx, ks):
+            for g0 in range(0, len(ks), 32):
+                grp = list(range(g0, min(g0 + 32, len(ks))))
+                for j, r in zip(grp, self._lloyd_wide(ctx, [C0_list[j] for j in grp], max_iter)):
+                    out[j] = r
+            return out
         for grp in self._pack_groups(ks, ctx.d):
             for j, r in zip(grp, self._lloyd_group(ctx, [C0_list[j] for j in grp], max_iter)):
                 out[j] = r
@@ -405,6 +418,193 @@ class GroupingEngine:
             centers = (C_all[lo:hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()  # _kmeans.py:1543-1546
             res.append(KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
                                     n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L]))
+        return res
+
+    # ------------------------------------------------------------------------------ a6, wide k-ranges on the tensor cores
+    def _use_wide(self, ctx, ks):
+        ok = (getattr(self.K, 'wide_lloyd', False) and ctx.d % 64 == 0 and ctx.d <= 4096 and max(ks) <= 100 and
+              ctx.e - ctx.b > 0)
+        if self.wide is not None:
+            if self.wide and not ok:
+                raise ValueError('wide Lloyd needs d % 64 == 0, d <= 4096 and k <= 100')
+            return bool(self.wide)
+        return ok and sum(ks) >= WIDE_MIN_SUM_K and ctx.e - ctx.b >= WIDE_MIN_ROWS
+
+    def _wide_operand(self, ctx):
+        """Row operand of the wide E-step, built once per fit context: fp16 hi / lo pieces of scale * Xc for this
+        rank's rows, row norms for the error bound, and the fixed-point unit 2^S of the M-step sums."""
+        if getattr(ctx, 'wide', None) is None:
+            K = self.K
+            Xs = ctx.Xc[ctx.b:ctx.e]
+            n = Xs.shape[0]
+            P = ((n + 255) // 256) * 256
+            amax = float(K.absmax(ctx.Xc).item())
+            amax = amax if amax > 0.0 else 1.0
+            scale = 2.0 ** math.floor(math.log2(2048.0 / amax))            # hi keeps 11 bits, lo the next 11
+            Xhi, Xlo = K.split_fp16(Xs, P, scale)
+            rown = K.zeros((P,), torch.float32)
+            rown[:n] = torch.sqrt(K.row_sqnorms(Xs))
+            S = 61 - math.ceil(math.log2(max(ctx.N, 2) * amax))           # |sum| <= N * amax * 2^S < 2^62
+            ctx.wide = dict(Xhi=Xhi, Xlo=Xlo, rown=rown, scale=scale, two_s=2.0 ** S, inv_two_s=2.0 ** -S, n=n)
+        return ctx.wide
+
+    @staticmethod
+    def _wide_columns(off, ks, batch):
+        """Column table of one launch: the centres of the labellings in `batch`, concatenated and padded to whole
+        256-column tiles.  info = flags | local index << 4 | labelling << 20 (flag 2: last centre of its labelling)."""
+        ncol = sum(ks[L] for L in batch)
+        Kp = ((ncol + 255) // 256) * 256
+        src = np.full(Kp, -1, dtype=np.int32)
+        info = np.zeros(Kp, dtype=np.uint32)
+        col0 = np.full(len(ks), -1, dtype=np.int32)
+        c = 0
+        for L in batch:
+            k = ks[L]
+            col0[L] = c
+            src[c:c + k] = np.arange(off[L], off[L] + k, dtype=np.int32)
+            info[c:c + k] = (np.arange(k, dtype=np.uint32) << 4) | np.uint32(L << 20)
+            info[c + k - 1] |= 2
+            c += k
+        return src, info, col0
+
+    def _wide_estep(self, ctx, C_all, off, ks, active, labels_new, fix, n_fix, cache):
+        """labels_new[L] = argmin_c |x - c|^2 for every active labelling L (SK/cluster/_k_means_lloyd.pyx:196-213):
+        tensor-core scores, then exact fp32 re-evaluation of the rows whose two best centres are closer than the
+        error bound of the tensor-core sum."""
+        K = self.K
+        wx = self._wide_operand(ctx)
+        eps = 3.0 * (ctx.d // 16) * 2.0 ** -23 * self.wide_eps_scale         # one ulp per accumulating MMA
+        plan = cache.get(active)
+        if plan is None:
+            batches, cur, ncol = [], [], 0
+            for L in range(len(ks)):
+                if not (active >> L) & 1:
+                    continue
+                if cur and ncol + ks[L] > WIDE_MAX_COLS:
+                    batches.append(cur)
+                    cur, ncol = [], 0
+                cur.append(L)
+                ncol += ks[L]
+            if cur:
+                batches.append(cur)
+            plan = []
+            for batch in batches:
+                src, info, col0 = self._wide_columns(off, ks, batch)
+                plan.append((self.to_device(src, torch.int32), torch.from_numpy(info.view(np.int32)).to(self.device), col0))
+            cache.clear()                  # the active set only ever shrinks: older plans are dead
+            cache[active] = plan
+        Xs = ctx.Xc[ctx.b:ctx.e]
+        n_fixed = []
+        for src, info, col0 in plan:
+            Bhi, Blo, tab, cmax = K.wide_pack_centres(C_all, src, info, wx['scale'])
+            n_fix.zero_()
+            K.wide_assign(wx['Xhi'], wx['Xlo'], wx['n'], Bhi, Blo, tab, wx['rown'], cmax, wx['scale'], eps, labels_new, fix, n_fix)
+            K.wide_refine(Xs, C_all, tab, off, col0, fix, n_fix, labels_new)
+            if self.profile:
+                n_fixed.append(n_fix.clone())
+        return n_fixed
+
+    def _lloyd_wide(self, ctx, C0s, max_iter):
+        """_lloyd_group with the E-step on the tensor cores and the M-step in exact fixed point, updated from the rows
+        that changed (csrc/lloyd_tc.cu).  Same stopping rules per labelling, same results."""
+        K, comm = self.K, self.comm
+        N, d, b, e = ctx.N, ctx.d, ctx.b, ctx.e
+        n = e - b
+        nL = len(C0s)
+        ks = [int(c.shape[0]) for c in C0s]
+        off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+        ktot = int(off[-1])
+        stride = 2 + max(ks)
+        wx = self._wide_operand(ctx)
+        two_s, inv_two_s = wx['two_s'], wx['inv_two_s']
+        C_all = torch.cat([c.contiguous() for c in C0s]).contiguous()
+        labels_all = torch.full((nL, N), -1, dtype=torch.int32, device=self.device)
+        labels_new = torch.zeros((nL, max(n, 1)), dtype=torch.int32, device=self.device)
+        Xs = ctx.Xc[b:e]
+        acc = K.zeros((ktot, d), torch.int64)
+        fix = K.empty((max(1, min(n * nL, (1 << 31) - 1)), 4), torch.int32)
+        n_fix = K.zeros((1,), torch.int32)
+        cap = max(1024, n // 50)                   # more changes than this: recompute the labelling's sums from the labels
+        items = K.empty((nL * cap, 4), torch.int32)
+        n_items = K.zeros((1,), torch.int32)
+        sum_groups = self._pack_groups(ks, 0)
+        cache = {}
+        active = (1 << nL) - 1
+        n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
+        log = dict(iters=0, fixed=[], listed=[])
+        for it in range(max_iter):
+            fx = self._wide_estep(ctx, C_all, off, ks, active, labels_new, fix, n_fix, cache)
+            cc = K.zeros((ktot + nL,), torch.int64)                            # counts | changed
+            counts, changed = cc[:ktot], cc[ktot:]
+            K.wide_count(labels_new, labels_all, b, n, off, active, counts, changed)
+            K.wide_commit(labels_new, labels_all, b, n, off, active, changed, cap, items, n_items)
+            K.wide_sums_delta(Xs, items, n_items, off, two_s, acc)
+            for grp in sum_groups:
+                if any((active >> L) & 1 for L in grp):
+                    K.wide_sums_full(Xs, labels_all, b, off, active, grp[0], grp[-1] + 1, changed, cap, two_s, acc)
+            if self.profile:
+                log['fixed'].append(fx)
+                log['listed'].append(n_items.clone())
+            acc_g = acc
+            if comm.active:
+                acc_g = acc.clone()
+                comm.allreduce_sum(acc_g)                                      # integers: exact in any order
+                comm.allreduce_sum(cc)
+            C_new, stats = K.wide_update(acc_g, inv_two_s, counts, changed, off, active, C_all, stride)
+            st = stats.cpu().numpy()                                           # the one D2H of the iteration
+            for L in range(nL):
+                if not (active >> L) & 1:
+                    continue
+                lo, hi = int(off[L]), int(off[L + 1])
+                stL = st[L, :2 + hi - lo]
+                if (stL[2:] == 0).any():                                       # empty cluster: relocate (rare)
+                    sums = acc_g[lo:hi].to(torch.float64) * inv_two_s
+                    cn, _, stL = self._relocate_empty(ctx, labels_all[L], C_all[lo:hi].contiguous(), sums,
+                                                      counts[lo:hi].contiguous(), changed[L:L + 1].contiguous(), stL)
+                    C_new[lo:hi] = cn
+                n_iter[L] = it + 1
+                if stL[1] == 0:                                                # labels == labels_old, _kmeans.py:723
+                    strict[L] = True
+                    active &= ~(1 << L)
+                    counts_fin[L] = counts[lo:hi].clone()
+                elif stL[0] <= ctx.tol:                                        # _kmeans.py:731-738
+                    active &= ~(1 << L)
+            C_all = C_new                                                      # _kmeans.py:721
+            log['iters'] = it + 1
+            if active == 0:
+                break
+        redo = sum(1 << L for L in range(nL) if not strict[L])
+        if redo:                                                               # _kmeans.py:742-754
+            self._wide_estep(ctx, C_all, off, ks, redo, labels_new, fix, n_fix, {})
+            counts = K.zeros((ktot,), torch.int64)
+            changed = K.zeros((nL,), torch.int64)
+            K.wide_count(labels_new, labels_new, 0, n, off, redo, counts, changed)
+            comm.allreduce_sum(counts)
+            for L in range(nL):
+                if not strict[L]:
+                    labels_all[L, b:e] = labels_new[L, :n]
+                    counts_fin[L] = counts[int(off[L]):int(off[L + 1])].clone()
+        if self.profile:
+            log['fixed'] = [[int(v.item()) for v in f] for f in log['fixed']]
+            log['listed'] = [int(v.item()) for v in log['listed']]
+            log.update(rows=n, labellings=nL, sum_k=ktot, cap=cap)
+            self.wide_stats = log
+        res = [None] * nL
+        C64_all = C_all.to(torch.float64)
+        for grp in sum_groups:                                                 # _k_means_common.pyx:94-124
+            g0, g1 = grp[0], grp[-1] + 1
+            lo0, hi0 = int(off[g0]), int(off[g1])
+            sub_off = (off[g0:g1 + 1] - off[g0]).astype(np.int32)
+            sq, _ = K.cluster_dispersion_multi(Xs, labels_all[g0:g1], b, sub_off, (1 << (g1 - g0)) - 1, C64_all[lo0:hi0].contiguous())
+            comm.allreduce_sum(sq)
+            sq_h = sq.cpu().numpy()
+            for L in grp:
+                lo, hi = int(off[L]) - lo0, int(off[L + 1]) - lo0
+                lab = labels_all[L]
+                comm.allgather_rows(lab, ctx.bounds)
+                centers = (C_all[lo0 + lo:lo0 + hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()   # _kmeans.py:1543-1546
+                res[L] = KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
+                                      n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L])
         return res
 
     def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):

@@ -190,6 +190,74 @@ class CudaKernels:
                 ptr(C_old), ptr(C_new), ptr(C64), ptr(stats), c_int(stats_stride), stream())
         return C_new, C64, stats
 
+    # ------------------------------------------------------------------ a6, wide form (csrc/lloyd_tc.cu)
+    wide_lloyd = True                  # the E-step of a whole k-range as one tcgen05 contraction
+
+    def split_fp16(self, X, n_pad, scale):
+        """scale * X = hi + lo in two fp16 matrices [n_pad, d] (rows past N are zero)."""
+        N, d = self._chk(X)
+        hi = self.empty((n_pad, d), torch.float16)
+        lo = self.empty((n_pad, d), torch.float16)
+        nv.call('vtf_dedup_pack', ptr(X), c_i64(N), c_int(d), c_i64(n_pad), c_f32(scale), ptr(hi), ptr(lo), stream())
+        return hi, lo
+
+    def wide_pack_centres(self, C_all, col_src, col_info, scale):
+        Kp, d = col_src.numel(), C_all.shape[1]
+        Bhi = self.empty((Kp, d), torch.float16)
+        Blo = self.empty((Kp, d), torch.float16)
+        tab = self.empty((Kp, 2), torch.float32)
+        cmax = self.empty((1,), torch.int32)
+        nv.call('vtf_wide_pack_centres', ptr(C_all), c_int(d), ptr(col_src), ptr(col_info), c_int(Kp), c_f32(scale), ptr(Bhi),
+                ptr(Blo), ptr(tab), ptr(cmax), stream())
+        return Bhi, Blo, tab, cmax
+
+    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, tab, rown, cmax, scale, eps, labels_new, fix, n_fix):
+        P, d = Xhi.shape
+        nv.call('vtf_wide_assign', ptr(Xhi), ptr(Xlo), c_i64(n_rows), c_i64(P), c_int(d), ptr(Bhi), ptr(Blo), c_int(Bhi.shape[0]),
+                ptr(tab), ptr(rown), ptr(cmax), c_f32(scale), c_f32(eps), ptr(labels_new), c_i64(labels_new.shape[1]), ptr(fix),
+                ptr(n_fix), fix.shape[0], stream())
+
+    def wide_refine(self, Xs, C_all, tab, k_off, col0, fix, n_fix, labels_new):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        keep2, c0 = self._koff(col0)
+        nv.call('vtf_wide_refine', ptr(Xs), c_int(d), ptr(C_all), ptr(tab), c_int(len(k_off) - 1), koff, c0, ptr(fix), ptr(n_fix),
+                fix.shape[0], ptr(labels_new), c_i64(labels_new.shape[1]), stream())
+
+    def wide_count(self, labels_new, labels_all, b, n, k_off, active, counts, changed):
+        keep, koff = self._koff(k_off)
+        nv.call('vtf_wide_count', ptr(labels_new), c_i64(labels_new.shape[1]), nv.c_vp(labels_all.data_ptr() + 4 * b),
+                c_i64(labels_all.shape[1]), c_i64(n), c_int(len(k_off) - 1), koff, active, ptr(counts), ptr(changed), stream())
+
+    def wide_commit(self, labels_new, labels_all, b, n, k_off, active, changed, cap, items, n_items):
+        keep, koff = self._koff(k_off)
+        nv.call('vtf_wide_commit', ptr(labels_new), c_i64(labels_new.shape[1]), nv.c_vp(labels_all.data_ptr() + 4 * b),
+                c_i64(labels_all.shape[1]), c_i64(n), c_int(len(k_off) - 1), koff, active, ptr(changed), c_i64(cap), ptr(items),
+                ptr(n_items), items.shape[0], stream())
+
+    def wide_sums_delta(self, Xs, items, n_items, k_off, two_s, acc):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        nv.call('vtf_wide_sums_delta', ptr(Xs), c_int(d), ptr(items), ptr(n_items), items.shape[0], c_int(len(k_off) - 1), koff,
+                two_s, ptr(acc), stream())
+
+    def wide_sums_full(self, Xs, labels_all, b, k_off, active, L0, L1, changed, cap, two_s, acc):
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        ws = self._workspace(nv.load().vtf_wide_sums_ws_bytes(int(k_off[L1] - k_off[L0]), d))
+        nv.call('vtf_wide_sums_full', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
+                c_int(len(k_off) - 1), koff, active, c_int(L0), c_int(L1), ptr(changed), c_i64(cap), two_s, ptr(acc), ptr(ws),
+                stream())
+
+    def wide_update(self, acc, inv_two_s, counts, changed, k_off, active, C_old, stats_stride):
+        ktot, d = C_old.shape
+        keep, koff = self._koff(k_off)
+        C_new = C_old.clone()                          # frozen labellings keep their centres
+        stats = self.zeros((len(k_off) - 1, stats_stride), torch.float64)
+        nv.call('vtf_wide_update', ptr(acc), inv_two_s, ptr(counts), ptr(changed), c_int(len(k_off) - 1), koff, active, c_int(d),
+                ptr(C_old), ptr(C_new), ptr(stats), c_int(stats_stride), stream())
+        return C_new, stats
+
     # ------------------------------------------------------------------ a3 / a1
     def cosine_classify(self, Xn, Rn, thr):
         N, d = self._chk(Xn)
