@@ -143,11 +143,12 @@ int vtf_lloyd_update_multi(const double* sums, const int64_t* counts, const int6
  * with another centre within eps * |x_row| * max|c| of the best score is appended to fix[] as
  * {row, L, mask lo, mask hi} (bit (index & 63) set for every candidate); *n_fix counts them (zeroed by the caller).
  * refine: decides the listed (row, L) with exact fp32 dot products (the arithmetic of vtf_lloyd_assign), so the
- * result equals the fp32 kernels'.  rown[P] = |x| per row (0 for padding).  Kp <= 2048 per launch.            */
+ * result equals the fp32 kernels'.  rown[P] = |x| per row (0 for padding).  Kp <= 2048 per launch; n_cols = columns
+ * in use (the last 256-column tile runs only ceil32 of what it holds: MMA N and epilogue shrink with it).      */
 int vtf_wide_pack_centres(const float* C_all, int d, const int32_t* col_src, const uint32_t* col_info, int Kp,
                           float scale, void* Bhi, void* Blo, float* tab, uint32_t* cmax2h, void* stream);
 int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P, int d, const void* Bhi,
-                    const void* Blo, int Kp, const float* tab, const float* rown, const uint32_t* cmax2h,
+                    const void* Blo, int Kp, int n_cols, const float* tab, const float* rown, const uint32_t* cmax2h,
                     float scale, float eps, int32_t* labels_new, int64_t label_stride, void* fix, uint32_t* n_fix,
                     uint32_t fix_cap, void* stream);
 int vtf_wide_refine(const float* X, int d, const float* C_all, const float* tab, int n_lab, const int32_t* k_off_h,

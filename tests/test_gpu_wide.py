@@ -42,7 +42,7 @@ def _fp32_labels(K, Xc, C_all, off, nL):
 
 
 @pytest.mark.parametrize('N,d,ks', [(5000, 512, [40, 33, 64]), (3001, 1024, [34, 100]), (2600, 192, [48, 40, 36, 35]),
-                                    (700, 64, [33])])
+                                    (700, 64, [33]), (4000, 256, [100, 100, 90]), (2304, 128, [100] * 21)])
 def test_wide_estep_equals_fp32_kernel_on_near_ties(engine, K, N, d, ks):
     rng = np.random.default_rng(N + d)
     nL, ktot = len(ks), sum(ks)
@@ -67,8 +67,9 @@ def test_wide_estep_equals_fp32_kernel_on_near_ties(engine, K, N, d, ks):
     engine._wide_estep(ctx, Cd, off, ks, (1 << nL) - 1, labels_new, fix, n_fix, {})
     n_flag = int(n_fix.item())
     want, _ = _fp32_labels(K, Xc, Cd, off, nL)
-    assert n_flag >= N // 3 - 5                                     # the planted ties were all caught
-    assert n_flag < N * nL // 2                                     # and ordinary rows were not
+    if ktot <= 2048:                                                    # (several launches: n_fix holds the last one's count)
+        assert n_flag >= N // 3 - 5                                     # the planted ties were all caught
+        assert n_flag < N * nL // 2                                     # and ordinary rows were not
     assert torch.equal(labels_new, want), 'mismatches: %d' % int((labels_new != want).sum().item())
 
 

@@ -43,7 +43,8 @@ struct WideParams {
     unsigned int fix_cap;
     long long n_rows;
     long long n_units;            // P / 256
-    int n_tiles;                  // Kp / 256
+    int n_tiles;                  // column tiles of 256; the last one is n_last wide
+    int n_last;                   // columns of the last tile, a multiple of 32: its MMAs and epilogue are that narrow
     int n_kb;                     // d / 64
     float inv;                    // 1 / scale^2
     float eps;                    // relative error bound of the tensor-core score, times |x| * max|c|
@@ -95,7 +96,8 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             for (long long u = pair0; u < prm.n_units; u += n_pairs) {
                 const int arow = (int)(u * 256 + cta_rank * 128);
                 for (int t = 0; t < prm.n_tiles; ++t) {
-                    const int brow = t * 256 + (int)cta_rank * 128;      // this CTA's half of the 256 centre rows
+                    // this CTA's half of the tile's centre rows (the box is always 128 rows; a narrow last tile uses the first n/2)
+                    const int brow = t * 256 + (int)cta_rank * ((t == prm.n_tiles - 1 ? prm.n_last : BN) / 2);
                     for (int kb = 0; kb < prm.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1u);
                         if (leader) mbar_expect_tx(full_bar(s), (uint32_t)kWStageBytes * 2);
@@ -120,6 +122,8 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     mbar_wait(tempty_bar(as), acc_ph ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+                    const uint32_t n_t = (uint32_t)(t == prm.n_tiles - 1 ? prm.n_last : BN);
+                    const uint32_t idesc = (1u << 4) | ((n_t >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
                     for (int kb = 0; kb < prm.n_kb; ++kb) {
                         mbar_wait(full_bar(s), ph);
                         tc_fence_after();
@@ -129,9 +133,9 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 #pragma unroll
                         for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
                             const uint64_t o = (uint64_t)(2 * k4);
-                            tc_mma_f16_pair(d_tmem, a_hi + o, b_hi + o, kIdescPair, (uint32_t)((kb | k4) != 0));
-                            tc_mma_f16_pair(d_tmem, a_hi + o, b_lo + o, kIdescPair, 1u);
-                            tc_mma_f16_pair(d_tmem, a_lo + o, b_hi + o, kIdescPair, 1u);
+                            tc_mma_f16_pair(d_tmem, a_hi + o, b_hi + o, idesc, (uint32_t)((kb | k4) != 0));
+                            tc_mma_f16_pair(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+                            tc_mma_f16_pair(d_tmem, a_lo + o, b_hi + o, idesc, 1u);
                         }
                         tc_commit_pair(empty_bar(s));
                         if (++s == kWStages) { s = 0; ph ^= 1u; }
@@ -159,8 +163,9 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             for (int t = 0; t < prm.n_tiles; ++t) {
                 mbar_wait(tfull_bar(as), acc_ph);
                 tc_fence_after();
+                const int n_chunks = (t == prm.n_tiles - 1 ? prm.n_last : BN) / 32;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < n_chunks; ++c) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (uint32_t)(as * BN + c * 32) + ((uint32_t)(q * 32) << 16);
                     VTF_TMEM_LD32(taddr, v);
@@ -502,12 +507,12 @@ int vtf_wide_pack_centres(const float* C_all, int d, const int32_t* col_src, con
 }
 
 int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P, int d, const void* Bhi, const void* Blo, int Kp,
-                    const float* tab, const float* rown, const uint32_t* cmax2h, float scale, float eps, int32_t* labels_new,
+                    int n_cols, const float* tab, const float* rown, const uint32_t* cmax2h, float scale, float eps, int32_t* labels_new,
                     int64_t label_stride, void* fix, uint32_t* n_fix, uint32_t fix_cap, void* stream) {
     VTF_REQUIRE(Xhi && Xlo && Bhi && Blo && tab && rown && cmax2h && labels_new && fix && n_fix && n_rows >= 0 && P >= n_rows &&
                     P % 256 == 0 && d >= 64 && d <= 4096 && d % 64 == 0 && Kp > 0 && Kp % 256 == 0 && Kp <= tc::kWMaxCols &&
-                    scale > 0.f && eps >= 0.f && label_stride >= n_rows,
-                "vtf_wide_assign (P % 256 == 0, d % 64 == 0, Kp % 256 == 0, Kp <= 2048)");
+                    n_cols > 0 && n_cols <= Kp && Kp - n_cols < 256 && scale > 0.f && eps >= 0.f && label_stride >= n_rows,
+                "vtf_wide_assign (P % 256 == 0, d % 64 == 0, Kp % 256 == 0, Kp <= 2048, Kp - 256 < n_cols <= Kp)");
     if (n_rows == 0) return VTF_OK;
     int rc = vtf_device_check();
     if (rc != VTF_OK) return rc;
@@ -527,7 +532,8 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
     prm.fix_cap = fix_cap;
     prm.n_rows = n_rows;
     prm.n_units = (n_rows + 255) / 256;
-    prm.n_tiles = Kp / 256;
+    prm.n_tiles = (n_cols + 255) / 256;
+    prm.n_last = ((n_cols - (prm.n_tiles - 1) * 256) + 31) / 32 * 32;
     prm.n_kb = d / tc::BK;
     prm.inv = 1.f / (scale * scale);
     prm.eps = eps;

@@ -490,15 +490,18 @@ class GroupingEngine:
             plan = []
             for batch in batches:
                 src, info, col0 = self._wide_columns(off, ks, batch)
-                plan.append((self.to_device(src, torch.int32), torch.from_numpy(info.view(np.int32)).to(self.device), col0))
+                plan.append((self.to_device(src, torch.int32), torch.from_numpy(info.view(np.int32)).to(self.device), col0,
+                             sum(ks[L] for L in batch)))
             cache.clear()                  # the active set only ever shrinks: older plans are dead
             cache[active] = plan
         Xs = ctx.Xc[ctx.b:ctx.e]
         n_fixed = []
-        for src, info, col0 in plan:
+        for src, info, col0, n_cols in plan:
             Bhi, Blo, tab, cmax = K.wide_pack_centres(C_all, src, info, wx['scale'])
             n_fix.zero_()
-            K.wide_assign(wx['Xhi'], wx['Xlo'], wx['n'], Bhi, Blo, tab, wx['rown'], cmax, wx['scale'], eps, labels_new, fix, n_fix)
+            with self.span('wide_assign', flops=2.0 * wx['n'] * n_cols * ctx.d):
+                K.wide_assign(wx['Xhi'], wx['Xlo'], wx['n'], Bhi, Blo, n_cols, tab, wx['rown'], cmax, wx['scale'], eps, labels_new,
+                              fix, n_fix)
             K.wide_refine(Xs, C_all, tab, off, col0, fix, n_fix, labels_new)
             if self.profile:
                 n_fixed.append(n_fix.clone())
@@ -524,7 +527,7 @@ class GroupingEngine:
         acc = K.zeros((ktot, d), torch.int64)
         fix = K.empty((max(1, min(n * nL, (1 << 31) - 1)), 4), torch.int32)
         n_fix = K.zeros((1,), torch.int32)
-        cap = max(1024, n // 50)                   # more changes than this: recompute the labelling's sums from the labels
+        cap = max(1024, n // 4)                    # more changes than this: recompute the labelling's sums from the labels
         items = K.empty((nL * cap, 4), torch.int32)
         n_items = K.zeros((1,), torch.int32)
         sum_groups = self._pack_groups(ks, 0)

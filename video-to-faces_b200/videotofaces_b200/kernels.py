@@ -211,10 +211,10 @@ class CudaKernels:
                 ptr(Blo), ptr(tab), ptr(cmax), stream())
         return Bhi, Blo, tab, cmax
 
-    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, tab, rown, cmax, scale, eps, labels_new, fix, n_fix):
+    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, n_cols, tab, rown, cmax, scale, eps, labels_new, fix, n_fix):
         P, d = Xhi.shape
         nv.call('vtf_wide_assign', ptr(Xhi), ptr(Xlo), c_i64(n_rows), c_i64(P), c_int(d), ptr(Bhi), ptr(Blo), c_int(Bhi.shape[0]),
-                ptr(tab), ptr(rown), ptr(cmax), c_f32(scale), c_f32(eps), ptr(labels_new), c_i64(labels_new.shape[1]), ptr(fix),
+                c_int(n_cols), ptr(tab), ptr(rown), ptr(cmax), c_f32(scale), c_f32(eps), ptr(labels_new), c_i64(labels_new.shape[1]), ptr(fix),
                 ptr(n_fix), fix.shape[0], stream())
 
     def wide_refine(self, Xs, C_all, tab, k_off, col0, fix, n_fix, labels_new):
