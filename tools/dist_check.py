@@ -34,18 +34,28 @@ def main():
         report['checks'].append(dict(name=name, ok=bool(cond), detail=detail))
         report['ok'] = report['ok'] and bool(cond)
 
-    for (N, d, ks, normalize) in [(8193, 512, [2, 3, 4], True), (6000, 768, [2, 5], False), (3001, 512, [2, 3], True)]:
+    cases = [(8193, 512, [2, 3, 4], True, None), (6000, 768, [2, 5], False, None), (3001, 512, [2, 3], True, None),
+             (20000, 512, list(range(2, 13)), True, True)]      # last: the wide (tensor-core) Lloyd path, forced
+    for (N, d, ks, normalize, wide) in cases:
         X = blobs(N, d, kc=6, noise=1.0, seed=1, normalize=normalize)
+        eng.wide = wide
         ctx, res = eng.kmeans_sweep(X, ks, 0)
+        eng.wide = None
         scores = eng.cluster_scores(ctx, res)
         if rank == 0:
             ref = RC.cluster_core(X, ks, 0, inits=[X[r.seeds] for r in res])
             for r, lab, inertia, n_iter, sc, rsc in zip(res, ref['labels'], ref['inertia'], ref['n_iter'], scores, ref['scores']):
-                agree = float((r.labels.cpu().numpy() == lab).mean())
-                check('labels N=%d k=%d' % (N, r.k), agree >= 0.9999, agree)
-                check('n_iter N=%d k=%d' % (N, r.k), r.n_iter == n_iter, (r.n_iter, n_iter))
-                check('inertia N=%d k=%d' % (N, r.k), abs(r.inertia - inertia) <= 1e-4 * inertia)
-                check('scores N=%d k=%d' % (N, r.k), np.allclose(sc[1:], rsc[1:], rtol=1e-4), (sc, rsc))
+                tag = 'N=%d k=%d%s' % (N, r.k, ' wide' if wide else '')
+                if r.k <= 6:
+                    agree = float((r.labels.cpu().numpy() == lab).mean())
+                    check('labels ' + tag, agree >= 0.9999, agree)
+                    check('n_iter ' + tag, r.n_iter == n_iter, (r.n_iter, n_iter))
+                    check('inertia ' + tag, abs(r.inertia - inertia) <= 1e-4 * inertia)
+                    check('scores ' + tag, np.allclose(sc[1:], rsc[1:], rtol=1e-4), (sc, rsc))
+                else:
+                    # more clusters than blobs: the split of a Gaussian blob is chaotic in the last ulp of a distance (any two
+                    # fp32 summation orders part ways), so only the quality of the optimum is comparable
+                    check('inertia ' + tag, abs(r.inertia - inertia) <= 2e-3 * inertia, (r.inertia, inertia))
             seeds_ok = [bool(np.array_equal(r.seeds, RC.kmeanspp_indices(X, r.k, 0))) for r in res]
             report.setdefault('seed_agreement', []).append(seeds_ok)
     X = plant_dupes(blobs(5000, 512, kc=4, seed=5), frac=20, seed=1)[0]
