@@ -140,20 +140,20 @@ int vtf_lloyd_update_multi(const double* sums, const int64_t* counts, const int6
  * *cmax2h = bits of max |c|^2 / 2.  Kp % 256 == 0.  The row operand comes from vtf_dedup_pack (same split).
  * assign: labels_new[L * label_stride + row] = argmin_c (|c|^2/2 - x.c) over the columns of labelling L, first
  * index on ties; scores from three fp16 MMAs (hi.hi + hi.lo + lo.hi), fp32 accumulate in TMEM.  Every (row, L)
- * with another centre within eps * |x_row| * max|c| of the best score is appended to fix[] as
- * {row, L, mask lo, mask hi} (bit (index & 63) set for every candidate); *n_fix counts them (zeroed by the caller).
- * refine: decides the listed (row, L) with exact fp32 dot products (the arithmetic of vtf_lloyd_assign), so the
- * result equals the fp32 kernels'.  rown[P] = |x| per row (0 for padding).  Kp <= 2048 per launch; n_cols = columns
- * in use (the last 256-column tile runs only ceil32 of what it holds: MMA N and epilogue shrink with it).      */
+ * with another centre within eps * |x_row| * max|c| of the best score is FLAGGED: the sign bit of its label word is
+ * set and bits [8, 24) hold the candidate mask (bit (index & 15) set for every candidate; k <= 256 per labelling).
+ * refine: decides the flagged (row, L) of the labellings with col0_h[L] >= 0 by exact fp32 dot products (the
+ * arithmetic of vtf_lloyd_assign) and clears the flag, so the result equals the fp32 kernels'; *n_fix (nullable)
+ * += pairs decided.  rown[P] = |x| per row (0 for padding).  Kp <= 2048 per launch; n_cols = columns in use (the
+ * last 256-column tile runs only ceil32 of what it holds: MMA N and epilogue shrink with it).                 */
 int vtf_wide_pack_centres(const float* C_all, int d, const int32_t* col_src, const uint32_t* col_info, int Kp,
                           float scale, void* Bhi, void* Blo, float* tab, uint32_t* cmax2h, void* stream);
 int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P, int d, const void* Bhi,
                     const void* Blo, int Kp, int n_cols, const float* tab, const float* rown, const uint32_t* cmax2h,
-                    float scale, float eps, int32_t* labels_new, int64_t label_stride, void* fix, uint32_t* n_fix,
-                    uint32_t fix_cap, void* stream);
+                    float scale, float eps, int32_t* labels_new, int64_t label_stride, void* stream);
 int vtf_wide_refine(const float* X, int d, const float* C_all, const float* tab, int n_lab, const int32_t* k_off_h,
-                    const int32_t* col0_h, const void* fix, const uint32_t* n_fix, uint32_t fix_cap,
-                    int32_t* labels_new, int64_t label_stride, void* stream);
+                    const int32_t* col0_h, int32_t* labels_new, int64_t label_stride, int64_t n, uint32_t* n_fix,
+                    void* stream);
 /* count: counts[k_off[L] + c] += rows of labelling L with new label c, changed[L] += rows whose new label differs
  * from the old one (SK/cluster/_kmeans.py:723), for the active labellings.  commit: labels_old = labels_new and,
  * for labellings with changed[L] <= cap, items[] += {row, L, old, new} (*n_items zeroed here).                 */

@@ -10,7 +10,7 @@
 //                        |c|^2/2 - x.c carries fp32-GEMM accuracy.  Epilogue: one thread = one row; running
 //                        argmin per labelling (first index on ties, _k_means_lloyd.pyx:205-213) plus the SET of
 //                        centres whose score lies within the error bound of the best one.  Rows with more than one
-//                        candidate go to a fix list ...
+//                        candidate are flagged (sign bit of the label, candidate mask beside it) ...
 //   wide_refine_kernel   ... and are decided by exact fp32 dot products in rowdot.cu's summation order, so the labels
 //                        equal those of the fp32 kernels.
 //   wide_count / commit  cluster sizes, "labels changed" counts (strict convergence, _kmeans.py:723) and the list of
@@ -38,9 +38,6 @@ struct WideParams {
     const unsigned int* cmax2h;   // float bits of max_c |c|^2 / 2
     int32_t* labels_new;          // [n_lab][label_stride]
     long long label_stride;
-    int4* fix;                    // {row, labelling, candidate mask lo, hi}
-    unsigned int* n_fix;
-    unsigned int fix_cap;
     long long n_rows;
     long long n_units;            // P / 256
     int n_tiles;                  // column tiles of 256; the last one is n_last wide
@@ -148,6 +145,9 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue: thread = row, all 256 columns of a tile
+        // One warp per scheduler, so the loop must be straight-line code with instruction-level parallelism: no branch per
+        // element (the stores at the end of a labelling are predicated PTX), best +- tol kept as running values so that the
+        // only loop-carried chain is compare -> select, and the TMEM load of the next 32 columns in flight behind the current.
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         int as = 0;
         uint32_t acc_ph = 0;
@@ -155,47 +155,58 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
         for (long long u = pair0; u < prm.n_units; u += n_pairs) {
             const long long row = u * 256 + cta_rank * 128 + q * 32 + lane;
             const float tol = prm.eps * prm.rown[row] * cmax;
-            const bool live = row < prm.n_rows;
-            float best = INFINITY;
-            int arg = 0;
-            unsigned long long mask = 0ull;
-            bool multi = false;
+            const uint32_t live = row < prm.n_rows ? 1u : 0u;
+            const uint32_t stride4 = (uint32_t)prm.label_stride * 4u, row4 = (uint32_t)row * 4u;
+            char* lab_base = reinterpret_cast<char*>(prm.labels_new);
+            float best = INFINITY, lo = INFINITY, hi = INFINITY;     // lo = best - tol, hi = best + tol
+            uint32_t arg = 0u, mask = 0u, multi = 0u;
+            auto process = [&](const uint32_t (&v)[32], const float2* tb) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 e = tb[j];
+                    const uint32_t info = __float_as_uint(e.y);
+                    const float s = fmaf(-__uint_as_float(v[j]), prm.inv, e.x);      // |c|^2/2 - x.c
+                    const float s_lo = s - tol, s_hi = s + tol;
+                    const uint32_t local = (info >> 4) & 0xffffu;
+                    const uint32_t bit = 0x100u << (local & 15u);     // candidate bits sit at [8, 24) of the label word
+                    const bool p_clear = s < lo;             // beats everything seen by more than the error bound
+                    const bool p_cand = s <= hi;             // within the bound of the best so far (indices 16 apart share a bit)
+                    const bool p_new = s < best;             // strict: the first index wins ties
+                    mask = p_clear ? bit : (p_cand ? (mask | bit) : mask);
+                    multi = p_clear ? 0u : (multi | (p_cand ? 0x80000000u : 0u));
+                    best = p_new ? s : best; lo = p_new ? s_lo : lo; hi = p_new ? s_hi : hi; arg = p_new ? local : arg;
+                    const uint32_t last = (info >> 1) & 1u;  // warp-uniform: last centre of this labelling
+                    // label word = index | candidate bits | flag; one predicated store, byte offset in 32 bits
+                    // (n_lab * label_stride * 4 < 2^32, checked on the host)
+                    const uint32_t ob = (info >> 20) * stride4 + row4;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
+                        "setp.ne.u32 p, %0, 0;\n\t"
+                        "cvt.u64.u32 a, %1;\n\t"
+                        "add.u64 a, a, %2;\n\t"
+                        "@p st.global.u32 [a], %3;\n\t}"
+                        ::"r"(last & live), "r"(ob), "l"(lab_base), "r"(arg | multi | (multi ? mask : 0u)));
+                    best = last ? INFINITY : best; lo = last ? INFINITY : lo; hi = last ? INFINITY : hi;
+                    mask = last ? 0u : mask; multi = last ? 0u : multi;
+                }
+            };
             for (int t = 0; t < prm.n_tiles; ++t) {
                 mbar_wait(tfull_bar(as), acc_ph);
                 tc_fence_after();
                 const int n_chunks = (t == prm.n_tiles - 1 ? prm.n_last : BN) / 32;
+                const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+                const float2* tb = s_tab + t * BN;
+                uint32_t va[32], vb[32];
+                VTF_TMEM_LD32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + (uint32_t)(as * BN + c * 32) + ((uint32_t)(q * 32) << 16);
-                    VTF_TMEM_LD32(taddr, v);
-                    VTF_TMEM_WAIT(v);
-                    const float2* tb = s_tab + t * BN + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {       // fully unrolled: v[] must stay in registers
-                        const float2 e = tb[j];
-                        const uint32_t info = __float_as_uint(e.y);
-                        const float s = fmaf(-__uint_as_float(v[j]), prm.inv, e.x);      // |c|^2/2 - x.c
-                        const int local = (int)((info >> 4) & 0xffffu);
-                        const unsigned long long bit = 1ull << (local & 63);
-                        if (s < best - tol) {            // beats everything seen by more than the error bound
-                            best = s; arg = local; mask = bit; multi = false;
-                        } else {
-                            if (s <= best + tol) { mask |= bit; multi = true; }   // (indices 64 apart share a mask bit)
-                            if (s < best) { best = s; arg = local; }
-                        }
-                        if (info & kColLast) {           // warp-uniform: last centre of this labelling
-                            if (live) {
-                                const int L = (int)(info >> 20);
-                                prm.labels_new[(long long)L * prm.label_stride + row] = arg;
-                                if (multi) {
-                                    const unsigned int slot = atomicAdd(prm.n_fix, 1u);
-                                    if (slot < prm.fix_cap)
-                                        prm.fix[slot] = make_int4((int)row, L, (int)(unsigned int)mask, (int)(unsigned int)(mask >> 32));
-                                }
-                            }
-                            best = INFINITY; arg = 0; mask = 0ull; multi = false;
-                        }
+                for (int c = 0; c < n_chunks; c += 2) {
+                    VTF_TMEM_WAIT(va);
+                    if (c + 1 < n_chunks) VTF_TMEM_LD32(taddr + (uint32_t)((c + 1) * 32), vb);
+                    process(va, tb + c * 32);
+                    if (c + 1 < n_chunks) {
+                        VTF_TMEM_WAIT(vb);
+                        if (c + 2 < n_chunks) VTF_TMEM_LD32(taddr + (uint32_t)((c + 2) * 32), va);
+                        process(vb, tb + (c + 1) * 32);
                     }
                 }
                 tc_fence_before();
@@ -258,40 +269,78 @@ struct WideSegs {
     unsigned int active;
 };
 
-// warp per fix-list entry: exact fp32 scores of the candidate centres, rowdot.cu's arithmetic (two FMA chains over
-// lane-strided float4, warp_sum, |c|^2/2 - x.c), first index wins
-__global__ void __launch_bounds__(256) wide_refine_kernel(const float* __restrict__ X, int d, const float* __restrict__ C_all,
-                                                          const float2* __restrict__ tab, const WideSegs sg, const int4* __restrict__ fix,
-                                                          const unsigned int* __restrict__ n_fix, unsigned int fix_cap,
-                                                          int32_t* __restrict__ labels_new, long long label_stride) {
+// Flagged (row, labelling) pairs -- sign bit of the label word, candidate bits (index & 15) at [8, 24) -- are decided here: exact fp32 scores of the candidate
+// centres in rowdot.cu's arithmetic (two FMA chains over lane-strided float4, warp_sum, |c|^2/2 - x.c), first index wins.
+// Warps scan 32 labels at a time and serve the flagged ones together.
+__global__ void __launch_bounds__(256, 2) wide_refine_kernel(const float* __restrict__ X, int d, const float* __restrict__ C_all,
+                                                          const float2* __restrict__ tab, const WideSegs sg,
+                                                          int32_t* __restrict__ labels_new, long long label_stride, long long n,
+                                                          unsigned int* __restrict__ n_fix) {
     const int lane = threadIdx.x & 31;
     const int nvec = d >> 2;
-    const unsigned int n = min(*n_fix, fix_cap);
     const bool two_chains = (d % 128 == 0) && (d / 128 <= 8);   // rowdot.cu: register-cached rows alternate two FMA chains
-    for (unsigned int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n; it += gridDim.x * 8) {
-        const int4 f = fix[it];
-        const int L = f.y;
-        const unsigned long long mask = ((unsigned long long)(unsigned int)f.w << 32) | (unsigned long long)(unsigned int)f.z;
+    const long long cpl = (n + 127) / 128;                       // 128-row chunks per labelling: 4 loads in flight per lane
+    const long long total = cpl * sg.n;
+    unsigned int flagged_total = 0;
+    for (long long ch = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); ch < total; ch += (long long)gridDim.x * 8) {
+        const int L = (int)(ch / cpl);
+        if (sg.col0[L] < 0) continue;                            // not in this launch
+        const long long r0 = (ch - (long long)L * cpl) * 128 + lane;
+        const long long at0 = (long long)L * label_stride + r0;
+        int v4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v4[u] = (r0 + 32 * u < n) ? labels_new[at0 + 32 * u] : 0;
         const int k = sg.off[L + 1] - sg.off[L];
-        const float4* xr = reinterpret_cast<const float4*>(X + (size_t)f.x * d);
-        float best = INFINITY;
-        int arg = 0;
-        for (int c = 0; c < k; ++c) {
-            if (!((mask >> (c & 63)) & 1ull)) continue;
-            const float4* cr = reinterpret_cast<const float4*>(C_all + (size_t)(sg.off[L] + c) * d);
-            float p = 0.f, q2 = 0.f;
-            int i = 0;
-            for (int v = lane; v < nvec; v += 32, ++i) {
-                const float4 a = __ldg(xr + v), b = __ldg(cr + v);
-                if (two_chains && (i & 1)) { q2 = fmaf(a.x, b.x, q2); q2 = fmaf(a.y, b.y, q2); q2 = fmaf(a.z, b.z, q2); q2 = fmaf(a.w, b.w, q2); }
-                else { p = fmaf(a.x, b.x, p); p = fmaf(a.y, b.y, p); p = fmaf(a.z, b.z, p); p = fmaf(a.w, b.w, p); }
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+            const int v = v4[0];
+            v4[0] = v4[1]; v4[1] = v4[2]; v4[2] = v4[3];
+            const long long r = r0 + 32 * u, at = at0 + 32 * u;
+            unsigned int m = __ballot_sync(0xffffffffu, v < 0);
+            if (!m) continue;
+            const unsigned int mine = ((unsigned int)v >> 8) & 0xffffu;
+            flagged_total += __popc(m);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned int mask = __shfl_sync(0xffffffffu, mine, src);
+                const long long row = r - lane + src;
+                const float4* xr = reinterpret_cast<const float4*>(X + (size_t)row * d);
+                float4 xc[8];                                    // the row, cached for d <= 1024 (rowdot.cu's DV path)
+                if (two_chains) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xc[i] = (lane + 32 * i < nvec) ? __ldg(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float best = INFINITY;
+                int arg = 0;
+                for (int c = 0; c < k; ++c) {
+                    if (!((mask >> (c & 15)) & 1u)) continue;
+                    const float4* cr = reinterpret_cast<const float4*>(C_all + (size_t)(sg.off[L] + c) * d);
+                    float p = 0.f, q2 = 0.f;
+                    if (two_chains) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (lane + 32 * i < nvec) {
+                                const float4 a = xc[i], b = __ldg(cr + lane + 32 * i);
+                                if (i & 1) { q2 = fmaf(a.x, b.x, q2); q2 = fmaf(a.y, b.y, q2); q2 = fmaf(a.z, b.z, q2); q2 = fmaf(a.w, b.w, q2); }
+                                else { p = fmaf(a.x, b.x, p); p = fmaf(a.y, b.y, p); p = fmaf(a.z, b.z, p); p = fmaf(a.w, b.w, p); }
+                            }
+                        }
+                    } else {
+                        for (int vv = lane; vv < nvec; vv += 32) {
+                            const float4 a = __ldg(xr + vv), b = __ldg(cr + vv);
+                            p = fmaf(a.x, b.x, p); p = fmaf(a.y, b.y, p); p = fmaf(a.z, b.z, p); p = fmaf(a.w, b.w, p);
+                        }
+                    }
+                    p = warp_sum(p + q2);
+                    const float s = tab[sg.col0[L] + c].x - p;
+                    if (s < best) { best = s; arg = c; }
+                }
+                if (lane == src) labels_new[at] = arg;
             }
-            p = warp_sum(p + q2);
-            const float s = tab[sg.col0[L] + c].x - p;
-            if (s < best) { best = s; arg = c; }
         }
-        if (lane == 0) labels_new[(long long)L * label_stride + f.x] = arg;
     }
+    if (lane == 0 && flagged_total && n_fix) atomicAdd(n_fix, flagged_total);
 }
 
 // grid (x, n_lab): cluster sizes of the new labels and the number of rows whose label changed
@@ -508,12 +557,14 @@ int vtf_wide_pack_centres(const float* C_all, int d, const int32_t* col_src, con
 
 int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P, int d, const void* Bhi, const void* Blo, int Kp,
                     int n_cols, const float* tab, const float* rown, const uint32_t* cmax2h, float scale, float eps, int32_t* labels_new,
-                    int64_t label_stride, void* fix, uint32_t* n_fix, uint32_t fix_cap, void* stream) {
-    VTF_REQUIRE(Xhi && Xlo && Bhi && Blo && tab && rown && cmax2h && labels_new && fix && n_fix && n_rows >= 0 && P >= n_rows &&
+                    int64_t label_stride, void* stream) {
+    VTF_REQUIRE(Xhi && Xlo && Bhi && Blo && tab && rown && cmax2h && labels_new && n_rows >= 0 && P >= n_rows &&
                     P % 256 == 0 && d >= 64 && d <= 4096 && d % 64 == 0 && Kp > 0 && Kp % 256 == 0 && Kp <= tc::kWMaxCols &&
                     n_cols > 0 && n_cols <= Kp && Kp - n_cols < 256 && scale > 0.f && eps >= 0.f && label_stride >= n_rows,
                 "vtf_wide_assign (P % 256 == 0, d % 64 == 0, Kp % 256 == 0, Kp <= 2048, Kp - 256 < n_cols <= Kp)");
     if (n_rows == 0) return VTF_OK;
+    VTF_REQUIRE(label_stride * 4096 < ((int64_t)1 << 43) && label_stride < ((int64_t)1 << 30) / kMaxSeg,
+                "vtf_wide_assign: label_stride * 32 labellings must stay below 2^30");
     int rc = vtf_device_check();
     if (rc != VTF_OK) return rc;
     CUtensorMap mxh, mxl, mch, mcl;
@@ -527,9 +578,6 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
     prm.cmax2h = cmax2h;
     prm.labels_new = labels_new;
     prm.label_stride = label_stride;
-    prm.fix = (int4*)fix;
-    prm.n_fix = n_fix;
-    prm.fix_cap = fix_cap;
     prm.n_rows = n_rows;
     prm.n_units = (n_rows + 255) / 256;
     prm.n_tiles = (n_cols + 255) / 256;
@@ -559,19 +607,19 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
 }
 
 int vtf_wide_refine(const float* X, int d, const float* C_all, const float* tab, int n_lab, const int32_t* k_off_h,
-                    const int32_t* col0_h, const void* fix, const uint32_t* n_fix, uint32_t fix_cap, int32_t* labels_new,
-                    int64_t label_stride, void* stream) {
-    VTF_REQUIRE(X && C_all && tab && k_off_h && col0_h && fix && n_fix && labels_new && d > 0 && d % 4 == 0 && n_lab > 0 &&
-                    n_lab <= kMaxSeg,
+                    const int32_t* col0_h, int32_t* labels_new, int64_t label_stride, int64_t n, uint32_t* n_fix, void* stream) {
+    VTF_REQUIRE(X && C_all && tab && k_off_h && col0_h && labels_new && d > 0 && d % 4 == 0 && n_lab > 0 &&
+                    n_lab <= kMaxSeg && n >= 0 && label_stride >= n,
                 "vtf_wide_refine");
-    if (fix_cap == 0) return VTF_OK;
+    if (n == 0) return VTF_OK;
     tc::WideSegs sg = {};
     sg.n = n_lab;
     for (int i = 0; i <= n_lab; ++i) sg.off[i] = k_off_h[i];
     for (int i = 0; i < n_lab; ++i) sg.col0[i] = col0_h[i];
-    const int grid = (int)min((int64_t)num_sms() * 8, (int64_t)(fix_cap + 7) / 8);
-    VTF_LAUNCH(tc::wide_refine_kernel, grid, 256, 0, stream, X, d, C_all, (const float2*)tab, sg, (const int4*)fix, n_fix, fix_cap,
-               labels_new, (long long)label_stride);
+    const int64_t chunks = ((n + 127) / 128) * n_lab;
+    const int grid = (int)min((int64_t)num_sms() * 8, (chunks + 7) / 8);
+    VTF_LAUNCH(tc::wide_refine_kernel, grid, 256, 0, stream, X, d, C_all, (const float2*)tab, sg, labels_new,
+               (long long)label_stride, (long long)n, n_fix);
     VTF_CHECK_LAST("vtf_wide_refine");
     return VTF_OK;
 }

@@ -39,8 +39,8 @@ SIGNATURES = {
     'vtf_lloyd_update_multi': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     'vtf_wide_pack_centres': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_wide_assign': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64,
-                                c_vp, c_vp, ctypes.c_uint32, c_vp]),
-    'vtf_wide_refine': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_i64, c_vp]),
+                                c_vp]),
+    'vtf_wide_refine': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     'vtf_wide_count': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     'vtf_wide_commit': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, ctypes.c_uint32, c_vp, c_i64, c_vp, c_vp,
                                 ctypes.c_uint32, c_vp]),

@@ -30,7 +30,7 @@ WIDE_MAX_COLS = 2048      # centre columns per launch (the kernel keeps their ta
 
 
 class KMeansResult:
-    __slots__ = ('k', 'labels', 'centers', 'inertia', 'n_iter', 'seeds', 'counts', 'strict')
+    __slots__ = ('k', 'labels', 'centers', 'inertia', 'n_iter', 'seeds', 'counts', 'strict', 'csums')
 
     def __init__(self, **kw):
         for n in self.__slots__:
@@ -467,7 +467,7 @@ class GroupingEngine:
             c += k
         return src, info, col0
 
-    def _wide_estep(self, ctx, C_all, off, ks, active, labels_new, fix, n_fix, cache):
+    def _wide_estep(self, ctx, C_all, off, ks, active, labels_new, n_fix, cache):
         """labels_new[L] = argmin_c |x - c|^2 for every active labelling L (SK/cluster/_k_means_lloyd.pyx:196-213):
         tensor-core scores, then exact fp32 re-evaluation of the rows whose two best centres are closer than the
         error bound of the tensor-core sum."""
@@ -495,17 +495,13 @@ class GroupingEngine:
             cache.clear()                  # the active set only ever shrinks: older plans are dead
             cache[active] = plan
         Xs = ctx.Xc[ctx.b:ctx.e]
-        n_fixed = []
+        n_fix.zero_()
         for src, info, col0, n_cols in plan:
             Bhi, Blo, tab, cmax = K.wide_pack_centres(C_all, src, info, wx['scale'])
-            n_fix.zero_()
             with self.span('wide_assign', flops=2.0 * wx['n'] * n_cols * ctx.d):
-                K.wide_assign(wx['Xhi'], wx['Xlo'], wx['n'], Bhi, Blo, n_cols, tab, wx['rown'], cmax, wx['scale'], eps, labels_new,
-                              fix, n_fix)
-            K.wide_refine(Xs, C_all, tab, off, col0, fix, n_fix, labels_new)
-            if self.profile:
-                n_fixed.append(n_fix.clone())
-        return n_fixed
+                K.wide_assign(wx['Xhi'], wx['Xlo'], wx['n'], Bhi, Blo, n_cols, tab, wx['rown'], cmax, wx['scale'], eps, labels_new)
+            K.wide_refine(Xs, C_all, tab, off, col0, labels_new, wx['n'], n_fix)
+        return n_fix.clone() if self.profile else None
 
     def _lloyd_wide(self, ctx, C0s, max_iter):
         """_lloyd_group with the E-step on the tensor cores and the M-step in exact fixed point, updated from the rows
@@ -525,7 +521,6 @@ class GroupingEngine:
         labels_new = torch.zeros((nL, max(n, 1)), dtype=torch.int32, device=self.device)
         Xs = ctx.Xc[b:e]
         acc = K.zeros((ktot, d), torch.int64)
-        fix = K.empty((max(1, min(n * nL, (1 << 31) - 1)), 4), torch.int32)
         n_fix = K.zeros((1,), torch.int32)
         cap = max(1024, n // 4)                    # more changes than this: recompute the labelling's sums from the labels
         items = K.empty((nL * cap, 4), torch.int32)
@@ -535,16 +530,21 @@ class GroupingEngine:
         active = (1 << nL) - 1
         n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
         log = dict(iters=0, fixed=[], listed=[])
-        for it in range(max_iter):
-            fx = self._wide_estep(ctx, C_all, off, ks, active, labels_new, fix, n_fix, cache)
-            cc = K.zeros((ktot + nL,), torch.int64)                            # counts | changed
-            counts, changed = cc[:ktot], cc[ktot:]
-            K.wide_count(labels_new, labels_all, b, n, off, active, counts, changed)
-            K.wide_commit(labels_new, labels_all, b, n, off, active, changed, cap, items, n_items)
+
+        def m_step(which, counts, changed):
+            # cluster sizes / change counts of labels_new, labels_all = labels_new, and the sums brought up to date: from the
+            # change list where few rows moved, from scratch otherwise (decided per labelling on the device)
+            K.wide_count(labels_new, labels_all, b, n, off, which, counts, changed)
+            K.wide_commit(labels_new, labels_all, b, n, off, which, changed, cap, items, n_items)
             K.wide_sums_delta(Xs, items, n_items, off, two_s, acc)
             for grp in sum_groups:
-                if any((active >> L) & 1 for L in grp):
-                    K.wide_sums_full(Xs, labels_all, b, off, active, grp[0], grp[-1] + 1, changed, cap, two_s, acc)
+                if any((which >> L) & 1 for L in grp):
+                    K.wide_sums_full(Xs, labels_all, b, off, which, grp[0], grp[-1] + 1, changed, cap, two_s, acc)
+        for it in range(max_iter):
+            fx = self._wide_estep(ctx, C_all, off, ks, active, labels_new, n_fix, cache)
+            cc = K.zeros((ktot + nL,), torch.int64)                            # counts | changed
+            counts, changed = cc[:ktot], cc[ktot:]
+            m_step(active, counts, changed)
             if self.profile:
                 log['fixed'].append(fx)
                 log['listed'].append(n_items.clone())
@@ -578,17 +578,21 @@ class GroupingEngine:
                 break
         redo = sum(1 << L for L in range(nL) if not strict[L])
         if redo:                                                               # _kmeans.py:742-754
-            self._wide_estep(ctx, C_all, off, ks, redo, labels_new, fix, n_fix, {})
+            self._wide_estep(ctx, C_all, off, ks, redo, labels_new, n_fix, {})
             counts = K.zeros((ktot,), torch.int64)
             changed = K.zeros((nL,), torch.int64)
-            K.wide_count(labels_new, labels_new, 0, n, off, redo, counts, changed)
+            m_step(redo, counts, changed)              # the sums follow the final labels: CH / DB reuse them
             comm.allreduce_sum(counts)
             for L in range(nL):
                 if not strict[L]:
-                    labels_all[L, b:e] = labels_new[L, :n]
                     counts_fin[L] = counts[int(off[L]):int(off[L + 1])].clone()
+        acc_g = acc
+        if comm.active:
+            acc_g = acc.clone()
+            comm.allreduce_sum(acc_g)
+        csums = acc_g.to(torch.float64) * inv_two_s     # per-cluster sums of the CENTRED rows, consistent with the labels
         if self.profile:
-            log['fixed'] = [[int(v.item()) for v in f] for f in log['fixed']]
+            log['fixed'] = [int(v.item()) for v in log['fixed']]
             log['listed'] = [int(v.item()) for v in log['listed']]
             log.update(rows=n, labellings=nL, sum_k=ktot, cap=cap)
             self.wide_stats = log
@@ -607,7 +611,8 @@ class GroupingEngine:
                 comm.allgather_rows(lab, ctx.bounds)
                 centers = (C_all[lo0 + lo:lo0 + hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()   # _kmeans.py:1543-1546
                 res[L] = KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
-                                      n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L])
+                                      n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L],
+                                      csums=csums[lo0 + lo:lo0 + hi])
         return res
 
     def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):
@@ -672,7 +677,7 @@ class GroupingEngine:
         """calinski_harabasz_score and davies_bouldin_score for one labelling (see ch_db_scores_multi)."""
         return self.ch_db_scores_multi(ctx, [labels], [k], [counts])[0]
 
-    def ch_db_scores_multi(self, ctx, labels_list, ks, counts_list=None):
+    def ch_db_scores_multi(self, ctx, labels_list, ks, counts_list=None, csums_list=None):
         """calinski_harabasz_score and davies_bouldin_score (SK/metrics/cluster/_unsupervised.py:333-487) for every
         labelling of the k-range with TWO passes over X in total: one for all per-cluster sums, one for all
         distances to the cluster means (the reference makes both passes once per k)."""
@@ -683,22 +688,30 @@ class GroupingEngine:
         counts_list = [c if c is not None else torch.bincount(l.to(torch.int64), minlength=k)
                        for c, l, k in zip(counts_list, labels_list, ks)]
         out = [None] * len(ks)
+        # Both scores are translation invariant.  When the fits left their per-cluster sums of the centred rows (the wide Lloyd
+        # path keeps them exact and consistent with the final labels) the first pass over X is not needed: work on Xc.
+        centred = csums_list is not None and all(c is not None for c in csums_list)
+        Xsrc = ctx.Xc if centred else ctx.X
+        gmean = (ctx.col_sum / ctx.N - ctx.mean32.to(torch.float64)) if centred else ctx.mean64
         for grp in self._pack_groups(ks, 0):
             gk = [ks[j] for j in grp]
             off = np.concatenate([[0], np.cumsum(gk)]).astype(np.int32)
             nL = len(grp)
             labels_all = torch.stack([labels_list[j] for j in grp]).contiguous()
             full = (1 << nL) - 1
-            sums = K.cluster_sums_multi(ctx.X[b:e], labels_all, b, off, full)
-            comm.allreduce_sum(sums)
+            if centred:
+                sums = torch.cat([csums_list[j] for j in grp]).contiguous()
+            else:
+                sums = K.cluster_sums_multi(Xsrc[b:e], labels_all, b, off, full)
+                comm.allreduce_sum(sums)
             cnt_all = torch.cat([counts_list[j] for j in grp]).to(torch.float64)
             means = (sums / cnt_all.clamp_min(1).unsqueeze(1)).contiguous()
-            sq, rt = K.cluster_dispersion_multi(ctx.X[b:e], labels_all, b, off, full, means)
+            sq, rt = K.cluster_dispersion_multi(Xsrc[b:e], labels_all, b, off, full, means)
             both = torch.cat([sq, rt])
             comm.allreduce_sum(both)
             ktot = int(off[-1])
             sq_h, rt_h = both[:ktot].cpu().numpy(), both[ktot:].cpu().numpy()
-            means_h, cnt_h, mean_h = means.cpu().numpy(), cnt_all.cpu().numpy(), ctx.mean64.cpu().numpy()
+            means_h, cnt_h, mean_h = means.cpu().numpy(), cnt_all.cpu().numpy(), gmean.cpu().numpy()
             for L, j in enumerate(grp):
                 lo, hi = int(off[L]), int(off[L + 1])
                 present = cnt_h[lo:hi] > 0
@@ -935,5 +948,5 @@ class GroupingEngine:
         counts = [r.counts for r in results]
         sil = self.silhouette_scores(ctx, labels, ks, counts, force=force)
         with self.span('ch_db'):
-            chdb = self.ch_db_scores_multi(ctx, labels, ks, counts)
+            chdb = self.ch_db_scores_multi(ctx, labels, ks, counts, [getattr(r, 'csums', None) for r in results])
         return [(r.k, float(s), ch, db) for r, s, (ch, db) in zip(results, sil, chdb)]

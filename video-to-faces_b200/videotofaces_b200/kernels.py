@@ -211,18 +211,18 @@ class CudaKernels:
                 ptr(Blo), ptr(tab), ptr(cmax), stream())
         return Bhi, Blo, tab, cmax
 
-    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, n_cols, tab, rown, cmax, scale, eps, labels_new, fix, n_fix):
+    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, n_cols, tab, rown, cmax, scale, eps, labels_new):
         P, d = Xhi.shape
         nv.call('vtf_wide_assign', ptr(Xhi), ptr(Xlo), c_i64(n_rows), c_i64(P), c_int(d), ptr(Bhi), ptr(Blo), c_int(Bhi.shape[0]),
-                c_int(n_cols), ptr(tab), ptr(rown), ptr(cmax), c_f32(scale), c_f32(eps), ptr(labels_new), c_i64(labels_new.shape[1]), ptr(fix),
-                ptr(n_fix), fix.shape[0], stream())
+                c_int(n_cols), ptr(tab), ptr(rown), ptr(cmax), c_f32(scale), c_f32(eps), ptr(labels_new), c_i64(labels_new.shape[1]),
+                stream())
 
-    def wide_refine(self, Xs, C_all, tab, k_off, col0, fix, n_fix, labels_new):
+    def wide_refine(self, Xs, C_all, tab, k_off, col0, labels_new, n_rows, n_fix):
         n, d = self._chk(Xs)
         keep, koff = self._koff(k_off)
         keep2, c0 = self._koff(col0)
-        nv.call('vtf_wide_refine', ptr(Xs), c_int(d), ptr(C_all), ptr(tab), c_int(len(k_off) - 1), koff, c0, ptr(fix), ptr(n_fix),
-                fix.shape[0], ptr(labels_new), c_i64(labels_new.shape[1]), stream())
+        nv.call('vtf_wide_refine', ptr(Xs), c_int(d), ptr(C_all), ptr(tab), c_int(len(k_off) - 1), koff, c0, ptr(labels_new),
+                c_i64(labels_new.shape[1]), c_i64(n_rows), ptr(n_fix), stream())
 
     def wide_count(self, labels_new, labels_all, b, n, k_off, active, counts, changed):
         keep, koff = self._koff(k_off)
