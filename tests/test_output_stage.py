@@ -1,0 +1,105 @@
+"""the threaded output stage leaves the same directory tree as the reference's
+per-file loops (grouping.py:78-84, 122-137; dupes.py:70-79), and embeddings that are still on the device go through
+the drop-in entry points without a host copy and give the same results as host arrays."""
+import os
+import os.path as osp
+
+import numpy as np
+import pytest
+
+from videotofaces_b200 import fileops
+
+
+def _tree(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            p = osp.join(d, f)
+            with open(p, 'rb') as fh:
+                out[osp.relpath(p, root)] = fh.read()
+    return out
+
+
+def _make(root, n):
+    os.makedirs(root)
+    paths = []
+    for i in range(n):
+        p = osp.join(root, 'face_%06d.jpg' % i)
+        with open(p, 'wb') as f:
+            f.write(b'jpeg%d' % i)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize('threads', ['1', '8'])
+def test_copy_move_remove_match_the_plain_loops(tmp_path, monkeypatch, threads):
+    monkeypatch.setenv('VTF_IO_THREADS', threads)
+    n = 1500                                   # > 2 chunks of 256, so the pool is used when threads > 1
+    paths = _make(str(tmp_path / 'a'), n)
+    labels = np.random.default_rng(0).integers(0, 5, n)
+    for j in range(5):
+        os.makedirs(tmp_path / 'a' / str(j))
+        os.makedirs(tmp_path / 'b' / str(j))
+    fileops.copy_files((p, osp.join(str(tmp_path / 'a'), str(l), osp.basename(p))) for p, l in zip(paths, labels))
+    fileops.move_files((p, osp.join(str(tmp_path / 'b'), str(l), osp.basename(p))) for p, l in zip(paths[:700], labels))
+    fileops.remove_files(paths[700:])
+    # the same with the reference's loops
+    import shutil
+    paths2 = _make(str(tmp_path / 'ref' / 'a'), n)
+    for j in range(5):
+        os.makedirs(tmp_path / 'ref' / 'a' / str(j))
+        os.makedirs(tmp_path / 'ref' / 'b' / str(j))
+    for p, l in zip(paths2, labels):
+        shutil.copyfile(p, osp.join(str(tmp_path / 'ref' / 'a'), str(l), osp.basename(p)))
+    for p, l in zip(paths2[:700], labels):
+        os.replace(p, osp.join(str(tmp_path / 'ref' / 'b'), str(l), osp.basename(p)))
+    for p in paths2[700:]:
+        os.remove(p)
+    got = {k: v for k, v in _tree(str(tmp_path)).items() if not k.startswith('ref' + os.sep)}
+    assert got == _tree(str(tmp_path / 'ref'))
+    assert len(got) == n + 700
+
+
+def test_errors_surface_after_the_batch(tmp_path, monkeypatch):
+    monkeypatch.setenv('VTF_IO_THREADS', '4')
+    paths = _make(str(tmp_path / 'a'), 1200)
+    os.remove(paths[900])
+    with pytest.raises(FileNotFoundError):
+        fileops.remove_files(paths)
+    assert not any(osp.exists(p) for p in paths)          # everything else was still removed
+
+
+def test_io_threads_env(monkeypatch):
+    monkeypatch.setenv('VTF_IO_THREADS', '3')
+    assert fileops.io_threads() == 3
+    monkeypatch.delenv('VTF_IO_THREADS')
+    assert fileops.io_threads() == 1                      # default: the reference's plain loop (measured faster here)
+
+
+@pytest.mark.gpu
+def test_device_resident_embeddings_go_through_the_drop_in_entry_points(tmp_path, engine, capsys):
+    import torch
+    from videotofaces_b200 import dupes, grouping
+    from videotofaces_b200.synth import blobs, plant_dupes
+    N = 3000
+    X = plant_dupes(blobs(N, 512, kc=4, seed=3), frac=25, seed=2)[0]
+    for sub in ('host', 'dev'):
+        os.makedirs(tmp_path / sub / 'faces')
+        for i in range(N):
+            (tmp_path / sub / 'faces' / ('%05d.jpg' % i)).write_bytes(b'x')
+    names = ['%05d.jpg' % i for i in range(N)]
+    Xh, goods_h = dupes.remove_dupes_overall(X, [str(tmp_path / 'host' / 'faces' / n) for n in names],
+                                             ('enc', 0.2, True, str(tmp_path / 'host')))
+    Xd, goods_d = dupes.remove_dupes_overall(torch.from_numpy(X).cuda(), [str(tmp_path / 'dev' / 'faces' / n) for n in names],
+                                             ('enc', 0.2, True, str(tmp_path / 'dev')))
+    assert isinstance(Xd, torch.Tensor) and Xd.is_cuda                     # no host copy of the survivors
+    assert np.array_equal(Xd.cpu().numpy(), Xh)
+    assert [osp.basename(g) for g in goods_d] == [osp.basename(g) for g in goods_h]
+    assert sorted(os.listdir(tmp_path / 'dev' / 'intermediate' / 'dupes3')) == sorted(os.listdir(tmp_path / 'host' / 'intermediate' / 'dupes3'))
+    a = grouping.cluster_labels(Xh, [2, 3, 4], 0)
+    b = grouping.cluster_labels(Xd, [2, 3, 4], 0)
+    assert all(np.array_equal(x, y) for x, y in zip(a['labels'], b['labels'])) and a['scores'] == b['scores']
+    R = X[:7].copy()
+    ih, _ = grouping.classify(Xh, R, [str(i) for i in range(7)], 0.8, False, None, None)
+    idv, _ = grouping.classify(Xd, torch.from_numpy(R).cuda(), [str(i) for i in range(7)], 0.8, False, None, None)
+    assert np.array_equal(ih, idv)

@@ -11,6 +11,7 @@ import os.path as osp
 
 import numpy as np
 
+from .fileops import move_files, remove_files
 from .runtime import get_engine
 
 
@@ -36,22 +37,22 @@ def remove_dupes_overall(X, filenames, dup_params):
     is_dup[idx] = True
     dupes = [fn for i, fn in enumerate(filenames) if is_dup[i]]                # dupes.py:66-67
     goods = [fn for i, fn in enumerate(filenames) if not is_dup[i]]
+    on_device = hasattr(X, 'is_cuda') and X.is_cuda                            # encoder output still on the GPU (section 8f item 2)
     if is_hash:
         X_kept = np.delete(np.asarray(X), idx, axis=0)                         # 64 ints per row: host bookkeeping
+    elif on_device:
+        X_kept = eng.delete_rows(X, idx) if idx.size else X.clone()            # stays in HBM for the grouping that follows
     else:
         X_kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
 
     face_dir = osp.join(out_dir, 'faces')
     if not save_dupes:                                                         # dupes.py:70-74
-        for fn in dupes:
-            os.remove(osp.join(face_dir, osp.basename(fn)))
+        remove_files(osp.join(face_dir, osp.basename(fn)) for fn in dupes)
     else:                                                                      # dupes.py:75-88
         mdigit, mname = ('2', 'hash_diff') if is_hash else ('3', 'distance')
         dup_dir = osp.join(out_dir, 'intermediate', 'dupes' + mdigit)
         os.makedirs(dup_dir, exist_ok=True)
-        for fn in dupes:
-            base = osp.basename(fn)
-            os.replace(osp.join(face_dir, base), osp.join(dup_dir, base))
+        move_files((osp.join(face_dir, osp.basename(fn)), osp.join(dup_dir, osp.basename(fn))) for fn in dupes)
         _write_dupes_log(osp.join(out_dir, 'intermediate', 'log_dupes' + mdigit + '.csv'), filenames, mins, inds, is_dup, mname)
 
     if not is_hash and idx.any():                                              # dupes.py:90-91

@@ -5,10 +5,10 @@ GroupingEngine (engine.py) instead of scikit-learn.
 """
 import os
 import os.path as osp
-import shutil
 
 import numpy as np
 
+from .fileops import copy_files, move_files, remove_files
 from .runtime import get_engine
 
 
@@ -50,8 +50,7 @@ def classify_faces(paths, X, model, classif_params, R=None):
     img_dir = osp.dirname(osp.abspath(paths[0]))
     for c in classes:
         os.makedirs(osp.join(img_dir, c), exist_ok=True)
-    for p, i in zip(paths, inds):
-        os.replace(p, osp.join(img_dir, classes[i], osp.basename(p)))
+    move_files((p, osp.join(img_dir, classes[i], osp.basename(p))) for p, i in zip(paths, inds))   # grouping.py:79-80
 
     print('Grouped %u images into %u folders:' % (len(paths), len(classes)))
     for i, c in enumerate(classes):
@@ -100,13 +99,11 @@ def cluster_faces(paths, X, cluster_params):
         sub = 'G%u' % k if len(clusters) > 1 else ''
         for j in range(k):
             os.makedirs(osp.join(img_dir, sub, str(j)), exist_ok=True)
-        for p, l in zip(paths, lab):
-            shutil.copyfile(p, osp.join(img_dir, sub, str(l), osp.basename(p)))
+        copy_files((p, osp.join(img_dir, sub, str(l), osp.basename(p))) for p, l in zip(paths, lab))  # grouping.py:129-130
         values, counts = np.unique(lab, return_counts=True)
         print((sub + ': ' if sub else '') + ', '.join('%u: %u' % (v, c) for v, c in zip(values, counts)))
     print()
-    for p in paths:
-        os.remove(p)
+    remove_files(paths)                                                                            # grouping.py:136-137
 
 
 def get_ground_truths(paths, out_dir, exclude_other):

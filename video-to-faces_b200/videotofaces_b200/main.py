@@ -16,6 +16,9 @@ from .dupes import remove_dupes_overall
 def _load_features(f):
     if isinstance(f, str):
         f = np.load(f)
+    if hasattr(f, 'is_cuda') and f.is_cuda:        # encoder output still in HBM: no trip through the host (section 8f item 2)
+        import torch
+        return f.detach().to(torch.float32).contiguous()
     return np.ascontiguousarray(f, dtype=np.float32)
 
 
