@@ -15,7 +15,8 @@ namespace vtf {
 
 constexpr int kMaxTrials = 8;
 
-__global__ void __launch_bounds__(256) kpp_dist_kernel(const float* __restrict__ X, int64_t N, int d,
+template <int TT, int R>   // TT = compile-time bound on the number of candidates, R = rows per warp and pass
+__global__ void __launch_bounds__(256, 2) kpp_dist_kernel(const float* __restrict__ X, int64_t N, int d,
                                                        const float* __restrict__ cand, int T,
                                                        const float* __restrict__ closest, float* __restrict__ out,
                                                        double* __restrict__ part) {
@@ -35,50 +36,73 @@ __global__ void __launch_bounds__(256) kpp_dist_kernel(const float* __restrict__
     }
     __syncthreads();
 
-    double pot[kMaxTrials];
+    double pot[TT];
 #pragma unroll
-    for (int t = 0; t < kMaxTrials; ++t) pot[t] = 0.0;
+    for (int t = 0; t < TT; ++t) pot[t] = 0.0;
 
-    int64_t row = (int64_t)blockIdx.x * 8 + warp;
-    const int64_t stride = (int64_t)gridDim.x * 8;
-    for (; row < N; row += stride) {
-        const float4* xr = reinterpret_cast<const float4*>(X + row * d);
-        double xx = 0.0, dot[kMaxTrials];
+    // R rows per warp and pass (4 for up to 4 candidates, 2 above: registers): every candidate float4 read from shared memory (and converted to fp64) serves R
+    // rows -- the kernel was bound by those reads (T wavefronts per row and float4), not by HBM or the fp64 pipe.
+    // Every row keeps its own accumulation order, so the results are bit-identical to the one-row form.
+    int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * R;
+    const int64_t stride = (int64_t)gridDim.x * 8 * R;
+    for (; row0 < N; row0 += stride) {
+        const float4* xr[R];
 #pragma unroll
-        for (int t = 0; t < kMaxTrials; ++t) dot[t] = 0.0;
+        for (int r = 0; r < R; ++r) xr[r] = reinterpret_cast<const float4*>(X + (row0 + r < N ? row0 + r : row0) * d);
+        double xx[R], dot[R][TT];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            xx[r] = 0.0;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) dot[r][t] = 0.0;
+        }
         for (int v = lane; v < nvec; v += 32) {
-            const float4 a = ldg_stream(xr + v);
-            const double ax = a.x, ay = a.y, az = a.z, aw = a.w;
-            xx = fma(ax, ax, xx); xx = fma(ay, ay, xx); xx = fma(az, az, xx); xx = fma(aw, aw, xx);
+            double a[R][4];
 #pragma unroll
-            for (int t = 0; t < kMaxTrials; ++t) {
+            for (int r = 0; r < R; ++r) {
+                const float4 f = ldg_stream(xr[r] + v);
+                a[r][0] = f.x; a[r][1] = f.y; a[r][2] = f.z; a[r][3] = f.w;
+                xx[r] = fma(a[r][0], a[r][0], xx[r]); xx[r] = fma(a[r][1], a[r][1], xx[r]);
+                xx[r] = fma(a[r][2], a[r][2], xx[r]); xx[r] = fma(a[r][3], a[r][3], xx[r]);
+            }
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
                 if (t < T) {
                     const float4 c = reinterpret_cast<const float4*>(sc + (size_t)t * d)[v];
-                    dot[t] = fma(ax, (double)c.x, dot[t]); dot[t] = fma(ay, (double)c.y, dot[t]);
-                    dot[t] = fma(az, (double)c.z, dot[t]); dot[t] = fma(aw, (double)c.w, dot[t]);
+                    const double cx = c.x, cy = c.y, cz = c.z, cw = c.w;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        dot[r][t] = fma(a[r][0], cx, dot[r][t]); dot[r][t] = fma(a[r][1], cy, dot[r][t]);
+                        dot[r][t] = fma(a[r][2], cz, dot[r][t]); dot[r][t] = fma(a[r][3], cw, dot[r][t]);
+                    }
                 }
             }
         }
-        xx = warp_sum(xx);
-        const float prev = closest ? __ldg(closest + row) : INFINITY;
 #pragma unroll
-        for (int t = 0; t < kMaxTrials; ++t) {
-            if (t < T) {
-                const double dt = warp_sum(dot[t]);
-                // ((-2 x.c) + |c|^2) + |x|^2 in fp64, then fp32, then clamp (pairwise.py:632-636, 413)
-                float dist = (float)((-2.0 * dt + s_cc[t]) + xx);
-                dist = fmaxf(dist, 0.f);
-                dist = fminf(dist, prev);
-                if (lane == 0) {
-                    out[(size_t)t * N + row] = dist;
-                    pot[t] += (double)dist;
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            const bool have = row < N;                                    // warp-uniform
+            const double xs = warp_sum(xx[r]);
+            const float prev = (closest && have) ? __ldg(closest + row) : INFINITY;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                if (t < T) {
+                    const double dt = warp_sum(dot[r][t]);
+                    // ((-2 x.c) + |c|^2) + |x|^2 in fp64, then fp32, then clamp (pairwise.py:632-636, 413)
+                    float dist = (float)((-2.0 * dt + s_cc[t]) + xs);
+                    dist = fmaxf(dist, 0.f);
+                    dist = fminf(dist, prev);
+                    if (lane == 0 && have) {
+                        out[(size_t)t * N + row] = dist;
+                        pot[t] += (double)dist;
+                    }
                 }
             }
         }
     }
     if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < kMaxTrials; ++t) s_pot[warp][t] = pot[t];
+        for (int t = 0; t < TT; ++t) s_pot[warp][t] = pot[t];
     }
     __syncthreads();
     if (threadIdx.x < T) {
@@ -383,8 +407,13 @@ int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T, co
     const size_t smem = (size_t)T * d * sizeof(float);
     VTF_REQUIRE(smem <= 64 * 1024, "vtf_kpp_dist: T*d too large");
     const int grid = kpp_grid();
-    VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "vtf_kpp_dist");
-    VTF_LAUNCH(kpp_dist_kernel, grid, 256, smem, stream, Xc, N, d, cand, T, closest, out, (double*)ws);
+    if (T <= 4) {
+        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "vtf_kpp_dist");
+        VTF_LAUNCH((kpp_dist_kernel<4, 4>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, out, (double*)ws);
+    } else {
+        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel<kMaxTrials, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "vtf_kpp_dist");
+        VTF_LAUNCH((kpp_dist_kernel<kMaxTrials, 2>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, out, (double*)ws);
+    }
     VTF_CHECK_LAST("vtf_kpp_dist");
     VTF_LAUNCH(reduce_parts_kernel, 1, 32, 0, stream, (const double*)ws, grid, T, pots, pots, T);
     VTF_CHECK_LAST("vtf_kpp_dist/reduce");
