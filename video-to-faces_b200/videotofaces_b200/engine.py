@@ -422,13 +422,14 @@ class GroupingEngine:
 
     # ------------------------------------------------------------------------------ a6, wide k-ranges on the tensor cores
     def _use_wide(self, ctx, ks):
+        # decided from global quantities only: every rank must take the same path (the paths differ in their collectives)
         ok = (getattr(self.K, 'wide_lloyd', False) and ctx.d % 64 == 0 and ctx.d <= 4096 and max(ks) <= 100 and
-              ctx.e - ctx.b > 0)
+              ctx.N >= self.comm.world)
         if self.wide is not None:
             if self.wide and not ok:
                 raise ValueError('wide Lloyd needs d % 64 == 0, d <= 4096 and k <= 100')
             return bool(self.wide)
-        return ok and sum(ks) >= WIDE_MIN_SUM_K and ctx.e - ctx.b >= WIDE_MIN_ROWS
+        return ok and sum(ks) >= WIDE_MIN_SUM_K and ctx.N >= WIDE_MIN_ROWS * self.comm.world
 
     def _wide_operand(self, ctx):
         """Row operand of the wide E-step, built once per fit context: fp16 hi / lo pieces of scale * Xc for this
