@@ -286,3 +286,121 @@ class FakeKernels:
             b = min([S[c] / cnt[c] for c in range(k) if c != own and cnt[c] > 0], default=np.inf)
             tot += self._sil(S[own], b, cnt[own])
         out_slot += tot
+
+    # ---- wide Lloyd path (csrc/lloyd_tc.cu): the contracts of the vtf_wide_* entry points in numpy
+    wide_lloyd = True
+
+    def split_fp16(self, X, n_pad, scale):
+        x = _np(X) * np.float32(scale)
+        hi = np.zeros((n_pad, x.shape[1]), dtype=np.float16)
+        lo = np.zeros_like(hi)
+        hi[:x.shape[0]] = x.astype(np.float16)
+        lo[:x.shape[0]] = (x - hi[:x.shape[0]].astype(np.float32)).astype(np.float16)
+        return torch.from_numpy(hi), torch.from_numpy(lo)
+
+    def wide_pack_centres(self, C_all, col_src, col_info, scale):
+        src, info = _np(col_src), _np(col_info).view(np.uint32)
+        c = _np(C_all)
+        Kp, d = src.size, c.shape[1]
+        rows = np.zeros((Kp, d), dtype=np.float32)
+        rows[src >= 0] = c[src[src >= 0]]
+        hi, lo = self.split_fp16(torch.from_numpy(rows), Kp, scale)
+        tab = np.zeros((Kp, 2), dtype=np.float32)
+        tab[:, 0] = np.where(src >= 0, 0.5 * (rows * rows).sum(1, dtype=np.float32), np.inf)
+        tab[:, 1] = np.where(src >= 0, info, info | 1).astype(np.uint32).view(np.float32)
+        cmax = np.array([tab[src >= 0, 0].max()], dtype=np.float32).view(np.int32)
+        return hi, lo, torch.from_numpy(tab), torch.from_numpy(cmax.copy())
+
+    def wide_assign(self, Xhi, Xlo, n_rows, Bhi, Blo, n_cols, tab, rown, cmax, scale, eps, labels_new):
+        xh, xl = _np(Xhi).astype(np.float64)[:n_rows], _np(Xlo).astype(np.float64)[:n_rows]
+        ch, cl = _np(Bhi).astype(np.float64), _np(Blo).astype(np.float64)
+        g = (xh @ ch.T + xh @ cl.T + xl @ ch.T).astype(np.float32)              # hi.hi + hi.lo + lo.hi
+        t = _np(tab)
+        info = t[:, 1].copy().view(np.uint32)
+        s_all = (t[None, :, 0] - g * np.float32(1.0 / (scale * scale))).astype(np.float32)
+        tol = (np.float32(eps) * _np(rown)[:n_rows] * np.sqrt(np.float32(2.0) * _np(cmax).view(np.float32)[0])).astype(np.float32)
+        out = _np(labels_new)
+        inf = np.float32(np.inf)
+        best = np.full(n_rows, inf, np.float32)
+        lo_, hi_ = best.copy(), best.copy()
+        arg = np.zeros(n_rows, np.uint32)
+        mask = np.zeros(n_rows, np.uint32)
+        multi = np.zeros(n_rows, bool)
+        n_cols32 = (n_cols + 31) // 32 * 32 if n_cols % 256 else n_cols
+        last_tile = (n_cols - 1) // 256 * 256
+        for j in range(min(Kp := t.shape[0], last_tile + ((n_cols - last_tile + 31) // 32) * 32)):
+            s = s_all[:, j]
+            local = np.uint32((int(info[j]) >> 4) & 0xffff)
+            bit = np.uint32(0x100 << (int(local) & 15))
+            p_clear, p_cand, p_new = s < lo_, s <= hi_, s < best
+            mask = np.where(p_clear, bit, np.where(p_cand, mask | bit, mask)).astype(np.uint32)
+            multi = np.where(p_clear, False, multi | p_cand)
+            best = np.where(p_new, s, best)
+            lo_ = np.where(p_new, s - tol, lo_)
+            hi_ = np.where(p_new, s + tol, hi_)
+            arg = np.where(p_new, local, arg).astype(np.uint32)
+            if (int(info[j]) >> 1) & 1:
+                L = int(info[j]) >> 20
+                word = np.where(multi, arg | mask | np.uint32(0x80000000), arg).astype(np.uint32)
+                out[L, :n_rows] = word.view(np.int32)
+                best[:] = inf; lo_[:] = inf; hi_[:] = inf
+                mask[:] = 0; multi[:] = False
+        del n_cols32
+
+    def wide_refine(self, Xs, C_all, tab, k_off, col0, labels_new, n_rows, n_fix):
+        x, c, t, lab = _np(Xs), _np(C_all), _np(tab), _np(labels_new)
+        for L in range(len(k_off) - 1):
+            if col0[L] < 0:
+                continue
+            k = int(k_off[L + 1] - k_off[L])
+            for r in np.nonzero(lab[L, :n_rows] < 0)[0]:
+                m = (int(lab[L, r]) >> 8) & 0xffff
+                cands = [cc for cc in range(k) if (m >> (cc & 15)) & 1]
+                s = [np.float32(t[col0[L] + cc, 0] - np.float32(np.dot(x[r], c[k_off[L] + cc]))) for cc in cands]
+                lab[L, r] = cands[int(np.argmin(s))]
+                n_fix += 1
+
+    def wide_count(self, labels_new, labels_all, b, n, k_off, active, counts, changed):
+        for L in range(len(k_off) - 1):
+            if (active >> L) & 1:
+                new = labels_new[L, :n].to(torch.int64)
+                counts[int(k_off[L]):int(k_off[L + 1])] += torch.bincount(new, minlength=int(k_off[L + 1] - k_off[L]))
+                changed[L] += int((new != labels_all[L, b:b + n].to(torch.int64)).sum())
+
+    def wide_commit(self, labels_new, labels_all, b, n, k_off, active, changed, cap, items, n_items):
+        n_items.zero_()
+        for L in range(len(k_off) - 1):
+            if not (active >> L) & 1:
+                continue
+            new, old = labels_new[L, :n], labels_all[L, b:b + n].clone()
+            rows = torch.nonzero(new != old).flatten()
+            if int(changed[L]) <= cap:
+                at = int(n_items[0])
+                for i, r in enumerate(rows.tolist()):
+                    items[at + i] = torch.tensor([r, L, int(old[r]), int(new[r])], dtype=torch.int32)
+                n_items += len(rows)
+            labels_all[L, b:b + n] = new
+
+    @staticmethod
+    def _fixed(x, two_s):
+        return torch.from_numpy(np.rint(_np(x).astype(np.float64) * two_s).astype(np.int64))
+
+    def wide_sums_delta(self, Xs, items, n_items, k_off, two_s, acc):
+        q = self._fixed(Xs, two_s)
+        for r, L, old, new in items[:int(n_items[0])].tolist():
+            acc[int(k_off[L]) + new] += q[r]
+            if old >= 0:
+                acc[int(k_off[L]) + old] -= q[r]
+
+    def wide_sums_full(self, Xs, labels_all, b, k_off, active, L0, L1, changed, cap, two_s, acc):
+        q = self._fixed(Xs, two_s)
+        n = Xs.shape[0]
+        for L in range(L0, L1):
+            if (active >> L) & 1 and int(changed[L]) > max(cap, 0):
+                lo, hi = int(k_off[L]), int(k_off[L + 1])
+                acc[lo:hi] = torch.zeros((hi - lo, q.shape[1]), dtype=torch.int64).index_add_(0, labels_all[L, b:b + n].to(torch.int64), q)
+
+    def wide_update(self, acc, inv_two_s, counts, changed, k_off, active, C_old, stats_stride):
+        sums = acc.to(torch.float64) * inv_two_s
+        C_new, _, stats = self.lloyd_update_multi(sums, counts, changed, k_off, active, C_old, stats_stride)
+        return C_new, stats

@@ -44,6 +44,15 @@ def _worker(rank, world, port, out):
         tc_sym = eng.silhouette_scores(ctx, [r.labels for r in res], ks, [r.counts for r in res], force='tc')
         eng.sym = None
         assert np.allclose(tc_sym, tc, rtol=1e-6), (tc_sym, tc)
+        # the wide (tensor-core E-step, fixed-point M-step) Lloyd path, forced: same fits through other exchange steps
+        eng.wide = True
+        _, wres = eng.kmeans_sweep(X, ks, 0, ctx=ctx)
+        eng.wide = None
+        for r, w in zip(res, wres):
+            assert torch.equal(r.labels, w.labels) and r.n_iter == w.n_iter and torch.equal(r.counts, w.counts), r.k
+            assert abs(r.inertia - w.inertia) <= 1e-9 * r.inertia
+        wide_chdb = eng.ch_db_scores_multi(ctx, [w.labels for w in wres], ks, [w.counts for w in wres], [w.csums for w in wres])
+        assert np.allclose(np.asarray(wide_chdb), np.asarray([e[2:] for e in exact]), rtol=1e-6)
         Xd = plant_dupes(X, frac=10, seed=1)[0]
         mins, inds, idx = eng.dedup(Xd, 0.2)
         dist_m, lab = eng.classify(X[:300], X[300:310], 0.5)

@@ -191,3 +191,28 @@ def test_rand_score_host_arithmetic(eng):
         assert eng.rand_score(a, torch.from_numpy(b)) == sklearn.metrics.rand_score(a, b)
     assert eng.rand_score(np.arange(6), torch.arange(6, dtype=torch.int32)) == 1.0      # every row its own cluster
     assert eng.rand_score(np.zeros(6, int), torch.zeros(6, dtype=torch.int32)) == 1.0   # nothing split
+
+
+@pytest.mark.parametrize('N,d,kc,ks', [(5000, 64, 4, [2, 3, 4]), (700, 128, 5, [2, 5, 9])])
+def test_wide_lloyd_host_loop(eng, N, d, kc, ks):
+    """engine._lloyd_wide (tensor-core E-step, fixed-point M-step from change lists) against the lock-step loop and the
+    scikit-learn oracle; 5000 rows put the first iteration over the change-list cap (sums from scratch) and the later
+    ones under it (delta), 700 rows run on change lists only."""
+    X = blobs(N, d, kc=kc, noise=1.0, seed=N % 7, normalize=False)
+    ctx, base = eng.kmeans_sweep(X, ks, 0)
+    eng.wide, eng.profile = True, True
+    _, wide = eng.kmeans_sweep(X, ks, 0, ctx=ctx)
+    stats = eng.wide_stats
+    eng.wide, eng.profile = None, False
+    ref = RC.cluster_core(X, ks, 0, inits=[X[r.seeds] for r in base], with_scores=False)
+    for r, w, lab, it in zip(base, wide, ref['labels'], ref['n_iter']):
+        assert torch.equal(r.labels, w.labels) and r.n_iter == w.n_iter == it and r.strict == w.strict
+        assert np.array_equal(w.labels.numpy(), lab)
+        assert torch.equal(r.counts, w.counts)
+        np.testing.assert_allclose(w.centers.numpy(), r.centers.numpy(), rtol=0, atol=1e-6)
+        want = torch.zeros_like(w.csums).index_add_(0, w.labels.to(torch.int64), ctx.Xc.to(torch.float64))
+        np.testing.assert_allclose(w.csums.numpy(), want.numpy(), rtol=0, atol=1e-7 * float(want.abs().max()))
+    assert stats['iters'] == max(w.n_iter for w in wide) and stats['cap'] == max(1024, N // 4)
+    assert stats['listed'][0] == (0 if N > 1024 else N * len(ks))      # first iteration: every row "changes" from -1
+    if max(w.n_iter for w in wide) > 2:
+        assert any(v > 0 for v in stats['listed'][1:])                 # later iterations run from the change lists
