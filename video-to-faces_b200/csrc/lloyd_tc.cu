@@ -49,7 +49,9 @@ struct WideParams {
 
 __global__ void __launch_bounds__(kWThreads, 1)
 wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
-                   const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl, const WideParams prm) {
+                   const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl,
+                   const __grid_constant__ CUtensorMap map_ch_last, const __grid_constant__ CUtensorMap map_cl_last,
+                   const WideParams prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t cta_rank = cluster_ctarank();
@@ -93,14 +95,20 @@ wide_assign_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             for (long long u = pair0; u < prm.n_units; u += n_pairs) {
                 const int arow = (int)(u * 256 + cta_rank * 128);
                 for (int t = 0; t < prm.n_tiles; ++t) {
-                    // this CTA's half of the tile's centre rows (the box is always 128 rows; a narrow last tile uses the first n/2)
-                    const int brow = t * 256 + (int)cta_rank * ((t == prm.n_tiles - 1 ? prm.n_last : BN) / 2);
+                    // this CTA's half of the tile's centre rows; a narrow last tile has its own maps whose box is n_last / 2 rows,
+                    // so a k-range with few centres (k = 2..6: 32 columns) streams the row operand and little else
+                    const bool last = t == prm.n_tiles - 1;
+                    const int half = (last ? prm.n_last : BN) / 2;
+                    const int brow = t * 256 + (int)cta_rank * half;
+                    const uint32_t tx = 2u * (uint32_t)(2 * kWBlock + 2 * half * BK * 2);       // both CTAs: A hi/lo + B hi/lo
+                    const CUtensorMap* mh = last ? &map_ch_last : &map_ch;
+                    const CUtensorMap* ml = last ? &map_cl_last : &map_cl;
                     for (int kb = 0; kb < prm.n_kb; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1u);
-                        if (leader) mbar_expect_tx(full_bar(s), (uint32_t)kWStageBytes * 2);
+                        if (leader) mbar_expect_tx(full_bar(s), tx);
                         const uint32_t dst = stage0 + (uint32_t)s * kWStageBytes;
-                        tma_load_2d_pair(&map_ch, full_bar(s), dst, kb * BK, brow);
-                        tma_load_2d_pair(&map_cl, full_bar(s), dst + kWBlock, kb * BK, brow);
+                        tma_load_2d_pair(mh, full_bar(s), dst, kb * BK, brow);
+                        tma_load_2d_pair(ml, full_bar(s), dst + kWBlock, kb * BK, brow);
                         tma_load_2d_pair(&map_xh, full_bar(s), dst + 2 * kWBlock, kb * BK, arow);
                         tma_load_2d_pair(&map_xl, full_bar(s), dst + 3 * kWBlock, kb * BK, arow);
                         if (++s == kWStages) { s = 0; ph ^= 1u; }
@@ -572,6 +580,11 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
     if ((rc = tc::make_operand_map(&mxl, Xlo, P, d, tc::BM, "vtf_wide_assign")) != VTF_OK) return rc;
     if ((rc = tc::make_operand_map(&mch, Bhi, Kp, d, tc::BM, "vtf_wide_assign")) != VTF_OK) return rc;
     if ((rc = tc::make_operand_map(&mcl, Blo, Kp, d, tc::BM, "vtf_wide_assign")) != VTF_OK) return rc;
+    const int n_tiles = (n_cols + 255) / 256;
+    const int n_last = ((n_cols - (n_tiles - 1) * 256) + 31) / 32 * 32;
+    CUtensorMap mchl, mcll;                       // the last tile's centre rows: boxes of n_last / 2 rows
+    if ((rc = tc::make_operand_map(&mchl, Bhi, Kp, d, n_last / 2, "vtf_wide_assign")) != VTF_OK) return rc;
+    if ((rc = tc::make_operand_map(&mcll, Blo, Kp, d, n_last / 2, "vtf_wide_assign")) != VTF_OK) return rc;
     tc::WideParams prm;
     prm.tab = (const float2*)tab;
     prm.rown = rown;
@@ -580,8 +593,8 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
     prm.label_stride = label_stride;
     prm.n_rows = n_rows;
     prm.n_units = (n_rows + 255) / 256;
-    prm.n_tiles = (n_cols + 255) / 256;
-    prm.n_last = ((n_cols - (prm.n_tiles - 1) * 256) + 31) / 32 * 32;
+    prm.n_tiles = n_tiles;
+    prm.n_last = n_last;
     prm.n_kb = d / tc::BK;
     prm.inv = 1.f / (scale * scale);
     prm.eps = eps;
@@ -600,7 +613,7 @@ int vtf_wide_assign(const void* Xhi, const void* Xlo, int64_t n_rows, int64_t P,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VTF_CUDA(cudaLaunchKernelEx(&cfg, tc::wide_assign_kernel, mxh, mxl, mch, mcl, prm), "vtf_wide_assign/launch");
+    VTF_CUDA(cudaLaunchKernelEx(&cfg, tc::wide_assign_kernel, mxh, mxl, mch, mcl, mchl, mcll, prm), "vtf_wide_assign/launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VTF_CHECK_LAST("vtf_wide_assign");
     return VTF_OK;

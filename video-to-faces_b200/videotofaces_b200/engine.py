@@ -23,7 +23,7 @@ TC_MIN_ROWS = 4096        # below this the exact fp32 silhouette kernel is used 
 TC_SYM_MIN_UNITS = 148    # symmetric (upper-triangle) sweep once there are at least 2 units of 256 rows per CTA pair
 TC_DEDUP_MIN_ROWS = 8192  # below this the fp32 FMA dedup kernel is used
 TC_MAX_CELLSUM_BYTES = 32 << 30
-WIDE_MIN_SUM_K = 33       # sum(k) of a k-range from which the E-step runs as one tensor-core contraction (lloyd_tc.cu);
+WIDE_MIN_SUM_K = int(os.environ.get('VTF_WIDE_MIN_SUM_K', '33'))   # sum(k) of a k-range from which the E-step runs as one tensor-core contraction (lloyd_tc.cu);
                           # below it a single register-tiled pass (rowtile.cu) is HBM-bound and cheaper
 WIDE_MIN_ROWS = 8192
 WIDE_MAX_COLS = 2048      # centre columns per launch (the kernel keeps their table in shared memory)
