@@ -98,7 +98,8 @@ def test_device_resident_embeddings_go_through_the_drop_in_entry_points(tmp_path
     assert sorted(os.listdir(tmp_path / 'dev' / 'intermediate' / 'dupes3')) == sorted(os.listdir(tmp_path / 'host' / 'intermediate' / 'dupes3'))
     a = grouping.cluster_labels(Xh, [2, 3, 4], 0)
     b = grouping.cluster_labels(Xd, [2, 3, 4], 0)
-    assert all(np.array_equal(x, y) for x, y in zip(a['labels'], b['labels'])) and a['scores'] == b['scores']
+    assert all(np.array_equal(x, y) for x, y in zip(a['labels'], b['labels']))
+    np.testing.assert_allclose(np.asarray(a['scores']), np.asarray(b['scores']), rtol=1e-6)   # the sweep's fp32 RED order varies
     R = X[:7].copy()
     ih, _ = grouping.classify(Xh, R, [str(i) for i in range(7)], 0.8, False, None, None)
     idv, _ = grouping.classify(Xd, torch.from_numpy(R).cuda(), [str(i) for i in range(7)], 0.8, False, None, None)
