@@ -93,10 +93,22 @@ def main():
     add('lloyd_assign_multi k=2..6', lambda: K.lloyd_assign_multi(X, C_all, off, 31, labels_all, 0, cnt_all, ch_all), B + 5 * N * 8, 2.0 * N * 20 * d)
     add('cluster_sums_multi k=2..6', lambda: K.cluster_sums_multi(X, labels_all, 0, off, 31), B + 5 * N * 4)
     add('cluster_dispersion_multi k=2..6', lambda: K.cluster_dispersion_multi(X, labels_all, 0, off, 31, C_all.double()), B + 5 * N * 4)
+    # the same E-step as one tcgen05 contraction (csrc/lloyd_tc.cu): centre pack + split-fp16 assign + exact refine of near ties
+    class _Ctx:
+        pass
+    wctx = _Ctx()
+    wctx.Xc, wctx.N, wctx.d, wctx.b, wctx.e, wctx.wide = X, N, d, 0, N, None
+    if d % 64 == 0:
+        lab_new = torch.zeros((len(ks), N), dtype=torch.int32, device='cuda')
+        n_fix = torch.zeros(1, dtype=torch.int32, device='cuda')
+        cache = {}
+        add('wide E-step k=2..6 (tcgen05: pack + assign + refine)',
+            lambda: eng._wide_estep(wctx, C_all, off, ks, 31, lab_new, n_fix, cache), B + 5 * N * 4, 2.0 * N * 20 * d)
     add('cosine_classify R=32', lambda: K.cosine_classify(X, R, 0.9), B + N * 32 * 4 + N * 8, 2.0 * N * 32 * d)
     nd = min(N, 50_000)
     Xd = X[:nd].contiguous()
     add('cosine_dedup N=%d (fp32 FMA)' % nd, lambda: K.cosine_dedup(Xd, 0, 1), None, float(nd) * nd * d)
+    add('cosine_dedup_tc N=%d (tcgen05, split fp16 + refine)' % nd, lambda: K.cosine_dedup_tc(Xd, 0, 1), None, float(nd) * nd * d)
     perm = torch.arange(N, device='cuda')
     P = ((N + 255) // 256) * 256
     perm = torch.cat([perm, torch.full((P - N,), -1, device='cuda', dtype=torch.int64)])
