@@ -198,3 +198,17 @@ def test_wide_fit_matches_sklearn_given_init(wide_engine):
         assert agree >= 0.9999, agree                                 # identical labels given the same initial centres
         assert abs(r.inertia - ref.inertia_) <= 1e-4 * ref.inertia_           # north_star tolerance
         assert r.n_iter == ref.n_iter_
+
+
+def test_wide_fit_empty_cluster_relocation(wide_engine):
+    """SK/cluster/tests/test_k_means.py:85-113 through the wide path on the device: a centre that attracts nothing gets the
+    farthest point (_k_means_common.pyx:167-211); the fixed-point sums and the labels they belong to stay untouched."""
+    eng = wide_engine
+    X = np.zeros((10, 64), dtype=np.float32)
+    X[:, 0] = [-10, -9.5, -9, -8.5, -8, -1, 1, 9, 9.5, 10]
+    init = np.zeros((3, 64), dtype=np.float32)
+    init[:, 0] = [-10, -10, -10]
+    ctx, res = eng.kmeans_sweep(X, [3], 0, inits=[init])
+    ref = RC.kmeans_fit(X, 3, 0, init=init)
+    assert np.array_equal(res[0].labels.cpu().numpy(), ref.labels_) and res[0].n_iter == ref.n_iter_
+    assert abs(res[0].inertia - ref.inertia_) <= 1e-5 * ref.inertia_

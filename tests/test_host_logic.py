@@ -91,6 +91,22 @@ def test_empty_cluster_relocation(eng):
     assert np.array_equal(res[0].labels.numpy(), ref.labels_)
 
 
+def test_empty_cluster_relocation_wide_path(eng):
+    """The same through engine._lloyd_wide: the relocation works on the fixed-point sums converted to fp64 and leaves them
+    (and the labels they belong to) untouched, as scikit-learn leaves labels_old untouched."""
+    X = np.zeros((10, 64), dtype=np.float32)
+    X[:, 0] = [-10, -9.5, -9, -8.5, -8, -1, 1, 9, 9.5, 10]
+    init = np.zeros((3, 64), dtype=np.float32)
+    init[:, 0] = [-10, -10, -10]
+    eng.wide = True
+    ctx, res = eng.kmeans_sweep(X, [3], 0, inits=[init])
+    eng.wide = None
+    ref = RC.kmeans_fit(X, 3, 0, init=init)
+    assert np.unique(res[0].labels.numpy()).size == 3
+    np.testing.assert_allclose(res[0].inertia, ref.inertia_, rtol=1e-5)
+    assert np.array_equal(res[0].labels.numpy(), ref.labels_) and res[0].n_iter == ref.n_iter_
+
+
 def test_dedup_and_classify_decode(eng):
     X = plant_dupes(blobs(400, 512, kc=4, noise=1.0, seed=0), frac=10, seed=1)[0]
     mins, inds, idx = eng.dedup(X, 0.2)
