@@ -326,9 +326,8 @@ class FakeKernels:
         arg = np.zeros(n_rows, np.uint32)
         mask = np.zeros(n_rows, np.uint32)
         multi = np.zeros(n_rows, bool)
-        n_cols32 = (n_cols + 31) // 32 * 32 if n_cols % 256 else n_cols
         last_tile = (n_cols - 1) // 256 * 256
-        for j in range(min(Kp := t.shape[0], last_tile + ((n_cols - last_tile + 31) // 32) * 32)):
+        for j in range(min(t.shape[0], last_tile + ((n_cols - last_tile + 31) // 32) * 32)):   # the last tile runs ceil32 wide
             s = s_all[:, j]
             local = np.uint32((int(info[j]) >> 4) & 0xffff)
             bit = np.uint32(0x100 << (int(local) & 15))
@@ -345,7 +344,6 @@ class FakeKernels:
                 out[L, :n_rows] = word.view(np.int32)
                 best[:] = inf; lo_[:] = inf; hi_[:] = inf
                 mask[:] = 0; multi[:] = False
-        del n_cols32
 
     def wide_refine(self, Xs, C_all, tab, k_off, col0, labels_new, n_rows, n_fix):
         x, c, t, lab = _np(Xs), _np(C_all), _np(tab), _np(labels_new)

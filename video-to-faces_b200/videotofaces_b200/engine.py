@@ -316,8 +316,6 @@ class GroupingEngine:
             K.lloyd_assign(Xs, C, ls, counts, n_changed)
             comm.allreduce_sum(counts)
             C64 = C.to(torch.float64)
-        elif comm.active:
-            pass
         sq, _, _ = K.cluster_dispersion(Xs, ls, C64)                           # _k_means_common.pyx:94-124
         comm.allreduce_sum(sq)
         comm.allgather_rows(labels, ctx.bounds)
