@@ -232,3 +232,44 @@ def test_wide_lloyd_host_loop(eng, N, d, kc, ks):
     assert stats['listed'][0] == (0 if N > 1024 else N * len(ks))      # first iteration: every row "changes" from -1
     if max(w.n_iter for w in wide) > 2:
         assert any(v > 0 for v in stats['listed'][1:])                 # later iterations run from the change lists
+
+
+def test_wide_column_table_layout():
+    """engine._wide_columns: every centre of every labelling of the batch appears exactly once, in order, with its local
+    index and labelling in the info word, the last centre of each labelling flagged, padding up to whole 256-column tiles."""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        nL = int(rng.integers(1, 32))
+        ks = [int(k) for k in rng.integers(2, 101, nL)]
+        off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+        batch = sorted(rng.choice(nL, size=int(rng.integers(1, nL + 1)), replace=False).tolist())
+        src, info, col0 = GroupingEngine._wide_columns(off, ks, batch)
+        n_cols = sum(ks[L] for L in batch)
+        assert src.size % 256 == 0 and src.size - n_cols < 256 and (src[n_cols:] == -1).all()
+        c = 0
+        for L in range(nL):
+            if L not in batch:
+                assert col0[L] == -1
+                continue
+            assert col0[L] == c
+            assert np.array_equal(src[c:c + ks[L]], np.arange(off[L], off[L + 1]))
+            assert np.array_equal((info[c:c + ks[L]] >> 4) & 0xffff, np.arange(ks[L]))
+            assert ((info[c:c + ks[L]] >> 20) == L).all()
+            assert np.array_equal((info[c:c + ks[L]] >> 1) & 1, np.arange(ks[L]) == ks[L] - 1)
+            c += ks[L]
+
+
+def test_pack_groups_and_fixed_point_unit(eng):
+    for ks, d in [([2, 3, 4, 5, 6], 512), (list(range(2, 33)), 1024), ([100, 100, 3], 0), ([7] * 70, 64)]:
+        groups = eng._pack_groups(ks, d)
+        assert [j for g in groups for j in g] == list(range(len(ks)))          # contiguous, complete, in order
+        for g in groups:
+            tot = sum(ks[j] for j in g)
+            assert len(g) <= 32 and (len(g) == 1 or (tot <= 96 and tot * d * 4 <= 160 * 1024))
+    # the fixed-point unit leaves head room: N * max|x| * 2^S < 2^62, and resolves far below fp32
+    X = blobs(3000, 64, kc=3, noise=1.0, seed=1, normalize=False) * np.float32(37.5)
+    ctx = eng.prepare(X)
+    wx = eng._wide_operand(ctx)
+    amax = float(np.abs(ctx.Xc.numpy()).max())
+    assert ctx.N * amax * wx['two_s'] < 2.0 ** 62 and wx['two_s'] * amax > 2.0 ** 36
+    assert wx['scale'] * amax <= 2048.0 and wx['scale'] * amax > 1024.0
