@@ -439,7 +439,7 @@ class GroupingEngine:
             P = ((n + 255) // 256) * 256
             amax = float(K.absmax(ctx.Xc).item())
             amax = amax if amax > 0.0 else 1.0
-            scale = 2.0 ** math.floor(math.log2(2048.0 / amax))            # hi keeps 11 bits, lo the next 11
+            scale = 2.0 ** min(60, math.floor(math.log2(2048.0 / amax)))   # hi keeps 11 bits, lo the next 11; 1/scale^2 stays a normal fp32
             Xhi, Xlo = K.split_fp16(Xs, P, scale)
             rown = K.zeros((P,), torch.float32)
             rown[:n] = torch.sqrt(K.row_sqnorms(Xs))
