@@ -273,3 +273,32 @@ def test_pack_groups_and_fixed_point_unit(eng):
     amax = float(np.abs(ctx.Xc.numpy()).max())
     assert ctx.N * amax * wx['two_s'] < 2.0 ** 62 and wx['two_s'] * amax > 2.0 ** 36
     assert wx['scale'] * amax <= 2048.0 and wx['scale'] * amax > 1024.0
+
+
+def test_wide_lloyd_more_than_32_labellings(eng):
+    """A k-range with more than 32 fits runs as several wide groups (the kernels take 32 labellings per call); every fit
+    must come back complete and self-consistent: labels in range, counts = bincount, sums = the labels' sums, centres =
+    means (strict convergence), and a final E-step with the returned centres must reproduce the labels."""
+    from oracle import restatement as RS
+    ks = list(range(2, 38))                                   # 36 labellings -> groups of 32 + 4
+    X = blobs(600, 64, kc=6, noise=0.6, seed=11, normalize=False)
+    eng.wide = True
+    ctx, res = eng.kmeans_sweep(X, ks, 0)
+    eng.wide = None
+    assert [r.k for r in res] == ks
+    Xc = ctx.Xc.numpy()
+    for r in res:
+        lab = r.labels.numpy()
+        assert lab.min() >= 0 and lab.max() < r.k and r.n_iter >= 1
+        assert np.array_equal(r.counts.numpy(), np.bincount(lab, minlength=r.k))
+        want = np.zeros((r.k, 64))
+        np.add.at(want, lab, Xc.astype(np.float64))
+        np.testing.assert_allclose(r.csums.numpy(), want, rtol=0, atol=1e-7 * np.abs(want).max())
+        if r.strict:
+            C = (r.centers.numpy() - ctx.mean32.numpy()[None, :])
+            np.testing.assert_allclose(C[r.counts.numpy() > 0], (want / np.maximum(r.counts.numpy(), 1)[:, None])[r.counts.numpy() > 0],
+                                       rtol=0, atol=2e-6)
+            again = RS.lloyd_assign(Xc, C.astype(np.float32))
+            assert (again == lab).mean() >= 0.995                  # (rows within an ulp of a bisector may flip)
+    inert = [r.inertia for r in res]
+    assert inert[0] > inert[5] > inert[-1]
