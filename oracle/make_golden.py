@@ -23,7 +23,7 @@ import numpy as np
 
 ROOT = osp.dirname(osp.dirname(osp.abspath(__file__)))
 sys.path.insert(0, osp.join(ROOT, 'video-to-faces_b200'))
-from videotofaces_b200.synth import blobs, blob_truth, plant_dupes  # noqa: E402
+from videotofaces_b200.synth import blobs, blob_truth, classify_faces_case, plant_dupes  # noqa: E402
 sys.path.insert(0, ROOT)
 from oracle.make_hashes import make_hashes  # noqa: E402
 
@@ -162,6 +162,78 @@ def golden_testmode(name, X, R, gt, thr, rstate, exclude_other):
     return dict(stdout=out)
 
 
+def _tree(root, skip=('ref',)):
+    out = []
+    for d, dirs, files in os.walk(root):
+        dirs[:] = sorted(x for x in dirs if not (d == root and x in skip))
+        out.extend(osp.relpath(osp.join(d, f), root) for f in sorted(files))
+    return sorted(out)
+
+
+def golden_classify_faces(name, X, R, names, thr):
+    """classify_faces (grouping.py:69-89) of the real reference: its encode_refs (the encoder network, off the path and
+    without weights offline) is replaced by a look-up of R; classify, the folder moves and the console text are its own."""
+    saved = ref_grouping.encode_refs
+    ref_grouping.encode_refs = lambda refs, model: R
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            paths = fake_faces(td, X.shape[0])
+            refs = [(c, ['unused.jpg']) for c in names]
+            _, out = quiet(ref_grouping.classify_faces, list(paths), X, None, (refs, thr, True, td))
+            tree = _tree(td)
+            with open(osp.join(td, 'faces', 'log_classification.csv')) as f:
+                log = f.read()
+    finally:
+        ref_grouping.encode_refs = saved
+    with open(osp.join(GOLD, name + '.log_classification.csv'), 'w') as f:
+        f.write(log)
+    return dict(stdout=out, tree=tree)
+
+
+def golden_classification_mode(name, X, R, names, dup_thr, oth_thr, save_dupes):
+    """video_to_faces(mode='grouping', group_mode='classification') of the real reference (main.py:13-82): argument
+    checks, ref_dir scan, face scan, dedup, classify_faces, 'Done'.  Only the two encoder calls are stubbed."""
+    import videotofaces.main as ref_main
+    saved = ref_main.get_encoder_model, ref_main.encode_faces, ref_grouping.encode_refs
+    ref_main.get_encoder_model = lambda style, mname, device: None
+    ref_main.encode_faces = lambda paths, model, bs, area: np.ascontiguousarray(X[[int(osp.basename(p)[1:7]) for p in paths]])
+    ref_grouping.encode_refs = lambda refs, model: R
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            fake_faces(td, X.shape[0])
+            for c in names + ['empty_class']:
+                os.makedirs(osp.join(td, 'ref', c))
+            for c in names:
+                with open(osp.join(td, 'ref', c, 'a.jpg'), 'wb') as f:
+                    f.write(b'x')
+            _, out = quiet(ref_main.video_to_faces, mode='grouping', style='live', out_dir=td, group_mode='classification',
+                           ref_dir=osp.join(td, 'ref'), enc_dup_thr=dup_thr, enc_oth_thr=oth_thr, save_dupes=save_dupes,
+                           group_log=True, device='cpu')
+            tree = _tree(td)
+            with open(osp.join(td, 'faces', 'log_classification.csv')) as f:
+                log = f.read()
+            out = out.replace(td, '<OUT>')
+    finally:
+        ref_main.get_encoder_model, ref_main.encode_faces, ref_grouping.encode_refs = saved
+    with open(osp.join(GOLD, name + '.log_classification.csv'), 'w') as f:
+        f.write(log)
+    return dict(stdout=out, tree=tree)
+
+
+def classify_faces_cases(man):
+    X, R, names = classify_faces_case()
+    gen = ("X=blobs(300,512,kc=5,noise=3,seed=6); C,_=blob_truth(300,512,kc=5,seed=6); "
+           "R=C+0.1*default_rng(3).standard_normal(C.shape,float32); classes anna..eve; ")
+    man['cases']['classify_faces_300x512'] = dict(gen=gen + 'thr=0.9', **golden_classify_faces('classify_faces_300x512', X, R, names, 0.9))
+    man['cases']['classify_faces_300x512_nothr'] = dict(gen=gen + 'thr=-1',
+                                                        **golden_classify_faces('classify_faces_300x512_nothr', X, R, names, -1))
+    Xd = plant_dupes(X, frac=10, seed=5)[0]
+    man['cases']['classification_mode_300x512'] = dict(
+        gen=gen + "X=plant_dupes(X,frac=10,seed=5)[0]; video_to_faces(mode='grouping', group_mode='classification', "
+                  "enc_dup_thr=0.2, enc_oth_thr=0.9, save_dupes=True); ref_dir has an extra image-less class folder",
+        **golden_classification_mode('classification_mode_300x512', Xd, R, names, 0.2, 0.9, True))
+
+
 def testmode_cases(man):
     # noise 5: the blobs overlap enough that classification, clustering and the 'other' threshold all make mistakes
     C, ids = blob_truth(500, 512, kc=5, seed=4)
@@ -177,6 +249,14 @@ def testmode_cases(man):
 
 
 def main():
+    if '--classify-faces-only' in sys.argv:    # add the classify_faces / classification-mode cases to an existing manifest
+        with open(osp.join(GOLD, 'MANIFEST.json')) as f:
+            man = json.load(f)
+        classify_faces_cases(man)
+        with open(osp.join(GOLD, 'MANIFEST.json'), 'w') as f:
+            json.dump(man, f, indent=1, sort_keys=True)
+        print(json.dumps({k: v for k, v in man['cases'].items() if k.startswith('classif')}, indent=1)[:4000])
+        return
     if '--testmode-only' in sys.argv:          # add the test_grouping cases to an existing manifest
         with open(osp.join(GOLD, 'MANIFEST.json')) as f:
             man = json.load(f)
@@ -231,6 +311,7 @@ def main():
         man['cases']['cluster_4rows_error'] = str(e)
 
     testmode_cases(man)
+    classify_faces_cases(man)
 
     with open(osp.join(GOLD, 'MANIFEST.json'), 'w') as f:
         json.dump(man, f, indent=1, sort_keys=True)

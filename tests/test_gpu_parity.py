@@ -138,6 +138,44 @@ def test_cluster_faces_golden(tmp_path, golden_dir, capsys, name):
     assert 'Grouped %u images into %s folders:' % (X.shape[0], '/'.join(str(k) for k in ks)) in out
 
 
+@pytest.mark.parametrize('name,thr', [('classify_faces_300x512', 0.9), ('classify_faces_300x512_nothr', -1)])
+def test_classify_faces_golden(tmp_path, golden_dir, capsys, name, thr):
+    """classify_faces (grouping.py:69-89) on the CUDA engine against the real reference: console text, folder of every
+    file, classification log."""
+    import dropin_cases as DC
+    DC.check_classify_faces(tmp_path, golden_dir, capsys, name, thr)
+
+
+def test_classification_mode_golden(tmp_path, golden_dir, capsys):
+    """video_to_faces(mode='grouping', group_mode='classification') (main.py:13-82): dedup, classify_faces, 'Done'."""
+    import dropin_cases as DC
+    DC.check_classification_mode(tmp_path, golden_dir, capsys)
+
+
+@pytest.mark.parametrize('thr', [-0.5, 0.0, None, -1, 2.5])
+def test_classify_threshold_switch(engine, thr):
+    """grouping.py:53 `if thr and thr != -1`: a negative threshold other than -1 is ON (every row -> 'other')."""
+    from videotofaces_b200.synth import classify_faces_case
+    X, R, names = classify_faces_case()
+    classes = list(names)
+    inds, _ = vgrouping.classify(X, R, classes, thr, False, None, None)
+    assert np.array_equal(inds, RC.classify_core(X, R, len(names), thr)[1])
+    assert (classes[-1] == 'other') == bool(thr and thr != -1)
+
+
+def test_zero_row_inputs(engine):
+    """Empty shards / empty inputs: every entry returns without touching memory."""
+    K = engine.K
+    E = torch.zeros((0, 512), dtype=torch.float32, device='cuda')
+    R = torch.from_numpy(blobs(5, 512)).cuda()
+    assert tuple(K.normalize_rows(E).shape) == (0, 512)
+    dist, lab = K.cosine_classify(E, K.normalize_rows(R), 0.5)
+    assert tuple(dist.shape) == (0, 5) and lab.numel() == 0
+    d2, l2 = engine.classify(E, R, 0.5)
+    assert d2.shape == (0, 5) and l2.shape == (0,)
+    assert engine.dedup(E, 0.2)[2].size == 0
+
+
 @pytest.mark.parametrize('N,d', [(500, 100), (5000, 72), (300, 20)])
 def test_unaligned_dimension_and_odd_sizes(engine, N, d):
     """Feature dimensions that are not multiples of 16/64 (padded with zero columns) through every entry."""
@@ -215,9 +253,8 @@ def test_sweep_vs_oracle_medium(engine, N, d, ks, normalize):
         assert r.n_iter == n_iter
         assert abs(r.inertia - inertia) <= 1e-4 * inertia
         np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-4)
-    seeds_ref = [RC.kmeanspp_indices(X, k, 0) for k in ks]
-    same = [np.array_equal(r.seeds, s) for r, s in zip(res, seeds_ref)]
-    print('k-means++ seed agreement with sklearn:', same)
+    for r, k in zip(res, ks):                                              # the seeding itself: same rows as sklearn's k-means++
+        assert np.array_equal(r.seeds, RC.kmeanspp_indices(X, k, 0)), (k, r.seeds)
 
 
 def test_full_size_properties_200k(engine):

@@ -46,9 +46,31 @@ def build_parser():
     return p
 
 
+def _init_ranks():
+    """`torchrun --nproc-per-node G -m videotofaces_b200 ...` runs one process per GPU: join the NCCL group before the
+    engine is built so that every phase shards its rows over the ranks (rank 0 owns files, logs and console).  A plain
+    `python -m videotofaces_b200` stays single-process like the reference."""
+    import os
+    if int(os.environ.get('WORLD_SIZE', '1')) <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return True
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    video_to_faces(**vars(args))
+    joined = _init_ranks()
+    try:
+        video_to_faces(**vars(args))
+    finally:
+        if joined:
+            import torch.distributed as dist
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

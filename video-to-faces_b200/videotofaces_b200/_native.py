@@ -120,9 +120,23 @@ def require_gpu():
     call('vtf_device_check')
 
 
+_empty_stub = {}
+
+
 def ptr(t):
-    """Device (or host) address of a torch tensor, None -> NULL."""
-    return None if t is None else c_vp(t.data_ptr())
+    """Device (or host) address of a torch tensor, None -> NULL.  A tensor without elements (a rank whose row shard is
+    empty) has no storage and data_ptr() == 0; the entry points treat NULL as a missing argument, so such a tensor is
+    passed as the address of a small per-device stub that no kernel dereferences (every entry point returns early or
+    launches nothing for zero rows)."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        import torch
+        stub = _empty_stub.get(t.device)
+        if stub is None:
+            stub = _empty_stub[t.device] = torch.zeros(64, dtype=torch.uint8, device=t.device)
+        return c_vp(stub.data_ptr())
+    return c_vp(t.data_ptr())
 
 
 def stream():

@@ -27,6 +27,14 @@ class Comm:
         if self.world == 1:
             self.active = False
 
+    @classmethod
+    def single(cls):
+        """A communicator of one rank regardless of the process group (engine.solo_if)."""
+        c = cls.__new__(cls)
+        import torch.distributed as dist
+        c._dist, c.active, c.group, c.rank, c.world = dist, False, None, 0, 1
+        return c
+
     def allreduce_sum(self, t):
         if self.active:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)

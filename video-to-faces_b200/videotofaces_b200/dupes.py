@@ -12,7 +12,9 @@ import os.path as osp
 import numpy as np
 
 from .fileops import move_files, remove_files
-from .runtime import get_engine
+from .runtime import get_engine, is_main, sync
+
+TIE_EPS = 1e-6        # |distance - threshold| at or below this is reported as a tie (BASELINE.json north_star)
 
 
 def _write_dupes_log(path, filenames, mins, inds, is_dup, measure_name):
@@ -46,7 +48,9 @@ def remove_dupes_overall(X, filenames, dup_params):
         X_kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
 
     face_dir = osp.join(out_dir, 'faces')
-    if not save_dupes:                                                         # dupes.py:70-74
+    if not is_main():                                                          # several ranks: rank 0 owns files, logs and console
+        pass
+    elif not save_dupes:                                                       # dupes.py:70-74
         remove_files(osp.join(face_dir, osp.basename(fn)) for fn in dupes)
     else:                                                                      # dupes.py:75-88
         mdigit, mname = ('2', 'hash_diff') if is_hash else ('3', 'distance')
@@ -55,6 +59,12 @@ def remove_dupes_overall(X, filenames, dup_params):
         move_files((osp.join(face_dir, osp.basename(fn)), osp.join(dup_dir, osp.basename(fn))) for fn in dupes)
         _write_dupes_log(osp.join(out_dir, 'intermediate', 'log_dupes' + mdigit + '.csv'), filenames, mins, inds, is_dup, mname)
 
-    if not is_hash and idx.any():                                              # dupes.py:90-91
-        print('Removed %u near-duplicates' % idx.shape[0])
+    if is_main():
+        if not is_hash and idx.any():                                          # dupes.py:90-91
+            print('Removed %u near-duplicates' % idx.shape[0])
+        if not is_hash and n > 1:
+            ties = int(np.count_nonzero(np.abs(mins[1:] - np.float32(threshold)) <= TIE_EPS))
+            if ties:                                                           # silent in the reference; north_star asks for it
+                print('NOTE: %u images have their nearest earlier image within %g of enc_dup_thr=%s' % (ties, TIE_EPS, str(threshold)))
+    sync()
     return X_kept, goods

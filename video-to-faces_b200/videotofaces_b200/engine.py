@@ -27,6 +27,7 @@ WIDE_MIN_SUM_K = int(os.environ.get('VTF_WIDE_MIN_SUM_K', '33'))   # sum(k) of a
                           # below it a single register-tiled pass (rowtile.cu) is HBM-bound and cheaper
 WIDE_MIN_ROWS = 8192
 WIDE_MAX_COLS = 2048      # centre columns per launch (the kernel keeps their table in shared memory)
+SOLO_ROWS_PER_RANK = 64   # fewer rows per rank than this: no sharding, every rank computes the whole input
 
 
 class KMeansResult:
@@ -76,6 +77,22 @@ class _Span:
         return False
 
 
+class _Solo:
+    def __init__(self, eng, on):
+        self.eng, self.on = eng, on
+
+    def __enter__(self):
+        if self.on:
+            self.saved = self.eng.comm
+            self.eng.comm = Comm.single()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.eng.comm = self.saved
+        return False
+
+
 class GroupingEngine:
     def __init__(self, kernels, comm=None):
         self.K = kernels
@@ -96,6 +113,16 @@ class GroupingEngine:
 
     def span(self, name, flops=0.0):
         return _Span(self, name, flops)
+
+    def solo_if(self, cond):
+        """Context manager: while active (and `cond` holds) the engine runs un-sharded -- every rank computes the whole
+        (tiny) problem redundantly with the same deterministic kernels, so all ranks hold the same result without an
+        exchange.  Used for inputs with fewer than SOLO_ROWS_PER_RANK rows per rank, where shards would be empty or
+        smaller than one tile.  `cond` must be derived from global quantities (every rank takes the same branch)."""
+        return _Solo(self, bool(cond) and self.comm.active)
+
+    def too_small_to_shard(self, n):
+        return n < SOLO_ROWS_PER_RANK * self.comm.world
 
     # ------------------------------------------------------------------------------ utilities
     def to_device(self, A, dtype=torch.float32):
@@ -143,6 +170,11 @@ class GroupingEngine:
         N = X.shape[0]
         if N == 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        with self.solo_if(self.too_small_to_shard(N)):
+            return self._dedup(X, threshold, force)
+
+    def _dedup(self, X, threshold, force):
+        N = X.shape[0]
         tc_ok = X.shape[1] <= 4096 and hasattr(self.K, 'cosine_dedup_tc')
         use_tc = (tc_ok and N >= TC_DEDUP_MIN_ROWS) if force is None else (force == 'tc')
         if use_tc and not tc_ok:
@@ -167,8 +199,9 @@ class GroupingEngine:
             raise ValueError('hash dedup expects [N,64] average hashes (dupes.py:11-15)')
         if H.shape[0] == 0:
             return np.zeros(0, np.uint16), np.zeros(0, np.int64), np.zeros(0, np.int64)
-        key = self.K.hash_dedup(torch.from_numpy(H).to(self.device), self.comm.rank, self.comm.world)
-        self.comm.allreduce_min(key)
+        with self.solo_if(self.too_small_to_shard(H.shape[0])):
+            key = self.K.hash_dedup(torch.from_numpy(H).to(self.device), self.comm.rank, self.comm.world)
+            self.comm.allreduce_min(key)
         key_h = key.cpu().numpy()
         mins = (key_h >> 32).astype(np.uint16)
         inds = (key_h & 0xffffffff).astype(np.int64)
@@ -189,10 +222,20 @@ class GroupingEngine:
         """grouping.py:51-56.  Returns (dist fp32 [N,R], inds int64 [N]) as numpy."""
         X = self._pad16(self.to_device(X))
         R = self._pad16(self.to_device(R))
+        with self.solo_if(self.too_small_to_shard(X.shape[0])):
+            dist, label = self._classify(X, R, thr)
+        on = bool(thr) and thr != -1                                          # grouping.py:53
+        if on and thr < 0:
+            # the kernel encodes "threshold off" as a negative value; a negative threshold other than -1 is ON in the
+            # reference and sends every row to 'other' (cosine distances are clipped to [0, 2], so min >= thr always)
+            label[:] = R.shape[0]                                             # grouping.py:55
+        return dist, label
+
+    def _classify(self, X, R, thr):
         Xn = self.K.normalize_rows(X)
         Rn = self.K.normalize_rows(R)
         b, e = self._my_rows(X.shape[0])
-        on = bool(thr) and thr != -1                                          # grouping.py:53
+        on = bool(thr) and thr != -1 and thr >= 0
         nR = R.shape[0]
         dist = self.K.zeros((X.shape[0], nR), torch.float32) if self.comm.active else None
         label = self.K.zeros((X.shape[0],), torch.int64) if self.comm.active else None

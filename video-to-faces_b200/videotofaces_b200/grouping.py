@@ -9,7 +9,15 @@ import os.path as osp
 import numpy as np
 
 from .fileops import copy_files, move_files, remove_files
-from .runtime import get_engine
+from .runtime import get_engine, is_main, sync
+
+TIE_EPS = 1e-6        # |distance - threshold| at or below this is reported as a tie (BASELINE.json north_star)
+
+
+def _say(*a):
+    """print on the rank that owns the console (every rank runs the arithmetic, rank 0 the side effects)."""
+    if is_main():
+        print(*a)
 
 
 def classify(X, R, classes, thr, log, paths, out_dir):
@@ -18,7 +26,10 @@ def classify(X, R, classes, thr, log, paths, out_dir):
     dist, inds = get_engine().classify(X, R, thr)
     if thr and thr != -1:
         classes.append('other')
-    if log:
+        ties = int(np.count_nonzero(np.abs(dist.min(axis=1) - np.float32(thr)) <= TIE_EPS)) if dist.size else 0
+        if ties:                                                               # silent in the reference; north_star asks for it
+            _say('NOTE: %u images have their nearest reference within %g of other_threshold=%s' % (ties, TIE_EPS, str(thr)))
+    if log and is_main():
         names = [osp.basename(p) for p in paths]
         with open(osp.join(out_dir, 'faces', 'log_classification.csv'), 'w') as f:
             extra = '(other_threshold=%s)' % str(thr) if thr else ''
@@ -40,22 +51,24 @@ def classify_faces(paths, X, model, classif_params, R=None):
     networks are outside this package); otherwise `model` is called like the reference does."""
     refs, thr, log, out_dir = classif_params
     classes = [c for (c, _) in refs]
-    print('Found %u classes in ref_dir: %s' % (len(classes), ', '.join(classes)))
-    print('Extracting features from reference images')
+    _say('Found %u classes in ref_dir: %s' % (len(classes), ', '.join(classes)))
+    _say('Extracting features from reference images')
     if R is None:
         R = encode_refs(refs, model)
-    print('Classifying images')
+    _say('Classifying images')
     inds, classes = classify(X, R, classes, thr, log, paths, out_dir)
 
-    img_dir = osp.dirname(osp.abspath(paths[0]))
-    for c in classes:
-        os.makedirs(osp.join(img_dir, c), exist_ok=True)
-    move_files((p, osp.join(img_dir, classes[i], osp.basename(p))) for p, i in zip(paths, inds))   # grouping.py:79-80
+    if is_main():
+        img_dir = osp.dirname(osp.abspath(paths[0]))
+        for c in classes:
+            os.makedirs(osp.join(img_dir, c), exist_ok=True)
+        move_files((p, osp.join(img_dir, classes[i], osp.basename(p))) for p, i in zip(paths, inds))   # grouping.py:79-80
 
-    print('Grouped %u images into %u folders:' % (len(paths), len(classes)))
+    _say('Grouped %u images into %u folders:' % (len(paths), len(classes)))
     for i, c in enumerate(classes):
-        print(c + ': ' + str(np.count_nonzero(inds == i)))
-    print()
+        _say(c + ': ' + str(np.count_nonzero(inds == i)))
+    _say()
+    sync()
 
 
 def cluster_labels(X, clusters, rstate, inits=None):
@@ -65,8 +78,9 @@ def cluster_labels(X, clusters, rstate, inits=None):
     eng = get_engine()
     n = X.shape[0]
     clusters = [c for c in clusters if c <= n]                                 # grouping.py:95
-    ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits)          # grouping.py:99-101
-    scores = eng.cluster_scores(ctx, results)                                  # grouping.py:104-108
+    with eng.solo_if(eng.too_small_to_shard(n)):
+        ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits)      # grouping.py:99-101
+        scores = eng.cluster_scores(ctx, results)                              # grouping.py:104-108
     best_k = max(scores, key=lambda s: s[1])[0] if scores else None            # grouping.py:116 (first max)
     return dict(clusters=clusters, labels=[r.labels.cpu().numpy() for r in results], scores=scores, best_k=best_k,
                 inertia=[r.inertia for r in results], n_iter=[r.n_iter for r in results],
@@ -78,10 +92,10 @@ def cluster_faces(paths, X, cluster_params):
     """grouping.py:92-137."""
     clusters, save_all, rstate, log, out_dir = cluster_params
     clusters = [c for c in clusters if c <= len(paths)]
-    print('Clustering images into %s groups' % ', '.join(str(cl) for cl in clusters))
+    _say('Clustering images into %s groups' % ', '.join(str(cl) for cl in clusters))
     res = cluster_labels(X, clusters, rstate)
     labels, scores = res['labels'], res['scores']
-    if log:
+    if log and is_main():
         with open(osp.join(out_dir, 'faces', 'log_clustering.csv'), 'w') as f:
             f.write('n_clusters,silhouette_score,calinski_harabasz_score,davies_bouldin_score\n')
             for score in scores:
@@ -91,19 +105,22 @@ def cluster_faces(paths, X, cluster_params):
         best_k = res['best_k']
         i = clusters.index(best_k)
         clusters, labels = [clusters[i]], [labels[i]]
-        print('The number of groups chosen: %u' % best_k)
+        _say('The number of groups chosen: %u' % best_k)
 
-    print('Grouped %u images into %s folders:' % (len(paths), '/'.join(str(cl) for cl in clusters)))
+    _say('Grouped %u images into %s folders:' % (len(paths), '/'.join(str(cl) for cl in clusters)))
     img_dir = osp.dirname(osp.abspath(paths[0]))
     for k, lab in zip(clusters, labels):
         sub = 'G%u' % k if len(clusters) > 1 else ''
-        for j in range(k):
-            os.makedirs(osp.join(img_dir, sub, str(j)), exist_ok=True)
-        copy_files((p, osp.join(img_dir, sub, str(l), osp.basename(p))) for p, l in zip(paths, lab))  # grouping.py:129-130
+        if is_main():
+            for j in range(k):
+                os.makedirs(osp.join(img_dir, sub, str(j)), exist_ok=True)
+            copy_files((p, osp.join(img_dir, sub, str(l), osp.basename(p))) for p, l in zip(paths, lab))  # grouping.py:129-130
         values, counts = np.unique(lab, return_counts=True)
-        print((sub + ': ' if sub else '') + ', '.join('%u: %u' % (v, c) for v, c in zip(values, counts)))
-    print()
-    remove_files(paths)                                                                            # grouping.py:136-137
+        _say((sub + ': ' if sub else '') + ', '.join('%u: %u' % (v, c) for v, c in zip(values, counts)))
+    _say()
+    if is_main():
+        remove_files(paths)                                                                        # grouping.py:136-137
+    sync()
 
 
 def get_ground_truths(paths, out_dir, exclude_other):
@@ -119,7 +136,7 @@ def get_ground_truths(paths, out_dir, exclude_other):
     if exclude_other:
         other_class = max(gt)
         keep = gt != other_class
-        print('Excluded %u images with "other" class' % np.count_nonzero(~keep))
+        _say('Excluded %u images with "other" class' % np.count_nonzero(~keep))
         paths = [f for f, kp in zip(paths, keep) if kp]
         gt = gt[keep]
     return gt, paths, max(gt), keep
@@ -132,9 +149,10 @@ def grouping_test_scores(X, R, gt, n_clusters, thr, rstate, classes=None, log=Fa
     classes = list(classes) if classes is not None else [str(i) for i in range(R.shape[0])]
     inds, _ = classify(X, R, classes, thr, log, paths, out_dir)                # grouping.py:146
     acc = np.count_nonzero(inds + 1 == gt) / gt.size                           # grouping.py:147
-    ctx, results = eng.kmeans_sweep(X, [int(n_clusters)], rstate)              # grouping.py:149
-    rand_scr = eng.rand_score(gt, results[0].labels)                           # grouping.py:150
-    silh_scr = eng.silhouette_scores(ctx, [results[0].labels], [results[0].k], [results[0].counts])[0]   # :151
+    with eng.solo_if(eng.too_small_to_shard(X.shape[0])):
+        ctx, results = eng.kmeans_sweep(X, [int(n_clusters)], rstate)          # grouping.py:149
+        rand_scr = eng.rand_score(gt, results[0].labels)                       # grouping.py:150
+        silh_scr = eng.silhouette_scores(ctx, [results[0].labels], [results[0].k], [results[0].counts])[0]   # :151
     return acc, rand_scr, float(np.float32(silh_scr)), results[0]
 
 
@@ -153,6 +171,7 @@ def test_grouping(paths, refs, test_params, X=None, R=None):
         X = np.asarray(X)[keep]
     acc, rand_scr, silh_scr, _ = grouping_test_scores(X, R, gt, n_clusters, None if exclude_other else thr, rstate,
                                                       classes=[c for (c, _) in refs], log=True, paths=paths, out_dir=out_dir)
-    print('%.4f / %.4f / %.4f' % (acc, rand_scr, silh_scr))
-    print('classification accuracy / rand score for clustering / silhouette score for clustering')
+    _say('%.4f / %.4f / %.4f' % (acc, rand_scr, silh_scr))
+    _say('classification accuracy / rand score for clustering / silhouette score for clustering')
+    sync()
 test_grouping.__test__ = False                    # a reference entry point, not a pytest test

@@ -11,6 +11,7 @@ import numpy as np
 from .prep import validate_args, get_clusters, get_class_ref, get_paths_for_grouping
 from .grouping import cluster_faces, classify_faces, test_grouping
 from .dupes import remove_dupes_overall
+from .runtime import is_main
 
 
 def _load_features(f):
@@ -96,3 +97,5 @@ def video_to_faces(input_path=None, input_ext=None,
     if group_mode == 'classification':                                         # main.py:78-80
         R = _load_features(ref_features) if ref_features is not None else None
         classify_faces(imgpaths, feats, encoder, (refs, enc_oth_thr, group_log, out_dir), R=R)
+    if is_main():
+        print('Done')                                                          # main.py:82

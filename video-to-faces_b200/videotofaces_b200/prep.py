@@ -5,6 +5,14 @@
 import os
 import os.path as osp
 
+
+def _say(*a):
+    """Console output comes from one process: under torchrun (one process per GPU) every rank runs the same argument
+    checks, rank 0 alone reports them."""
+    if int(os.environ.get('RANK', '0')) == 0:
+        print(*a)
+
+
 IMG_EXTENSIONS = ('.jpg', '.jpeg', '.png', '.ppm', '.bmp', '.pgm', '.tif', '.tiff', '.webp')
 
 _CHOICES = {
@@ -30,7 +38,7 @@ def get_img_paths(target_dir):
 def _known(val, arg_name, options):
     if val in options:
         return True
-    print('ERROR: unknown %s. Available options are %s' % (arg_name, ', '.join('"' + v + '"' for v in options)))
+    _say('ERROR: unknown %s. Available options are %s' % (arg_name, ', '.join('"' + v + '"' for v in options)))
     return False
 
 
@@ -49,7 +57,7 @@ def validate_args(mode, input_path, out_dir, style, group_mode, video_reader, de
     if not input_path and mode == 'grouping' and not out_dir:
         problems.append('ERROR: for grouping, please specify either out_dir or the same input_path used during detection')
     for p in problems:
-        print(p)
+        _say(p)
     ok = not problems
     for name, val in (('style', style), ('group_mode', group_mode), ('video_reader', video_reader)):
         ok = ok and _known(val, name, _CHOICES[name])
@@ -75,7 +83,7 @@ def get_clusters(c):
             lo, hi = int(parts[0]), int(parts[1])
             if 0 < lo < hi:
                 return list(range(lo, hi + 1))
-    print('ERROR: incorrent value for clusters. Please specify a natural number or a string either as an '
+    _say('ERROR: incorrent value for clusters. Please specify a natural number or a string either as an '
           'enumeration "C1,C2,C3,C4" or a range "A-B" where 0 < A < B')
     return None
 
@@ -87,18 +95,18 @@ def get_class_ref(ref_dir, out_dir):
     if not ref_dir:
         guess = osp.join(out_dir, 'ref')
         if not osp.isdir(guess):
-            print('ERROR: for group_mode="classification", ref_dir needs to be specified')
-            print(explanation)
+            _say('ERROR: for group_mode="classification", ref_dir needs to be specified')
+            _say(explanation)
             return None
-        print('NOTE: ref_dir is unspecified, but found "ref" folder inside out_dir. Will search for reference images there')
+        _say('NOTE: ref_dir is unspecified, but found "ref" folder inside out_dir. Will search for reference images there')
         ref_dir = guess
     if not osp.isdir(ref_dir):
-        print('ERROR: specified ref_dir doesn\'t exist or isn\'t a directory. Please provide a valid path to a directory')
+        _say('ERROR: specified ref_dir doesn\'t exist or isn\'t a directory. Please provide a valid path to a directory')
         return None
     classes = sorted(e.name for e in os.scandir(ref_dir) if e.is_dir())
     if not classes:
-        print('ERROR: specified ref_dir doesn\'t contain any subfolders')
-        print(explanation)
+        _say('ERROR: specified ref_dir doesn\'t contain any subfolders')
+        _say(explanation)
         return None
     refs, warnings = [], []
     for c in classes:
@@ -109,11 +117,11 @@ def get_class_ref(ref_dir, out_dir):
             warnings.append('WARNING: ref_dir\'s subfolder "%s" doesn\'t contain any images. During classification, '
                             'this class will be ignored' % c)
     if not refs:
-        print('ERROR: none of the ref_dir\'s subfolders contain any images')
-        print('Supported extensions are: %s' % ', '.join(IMG_EXTENSIONS))
+        _say('ERROR: none of the ref_dir\'s subfolders contain any images')
+        _say('Supported extensions are: %s' % ', '.join(IMG_EXTENSIONS))
         return None
     for w in warnings:
-        print(w)
+        _say(w)
     return refs
 
 
@@ -122,7 +130,7 @@ def get_paths_for_grouping(out_dir):
     for tdir in (osp.join(out_dir, 'faces'), out_dir):
         paths = get_img_paths(tdir) if osp.isdir(tdir) else []
         if paths:
-            print('Found %u images at: %s' % (len(paths), tdir))
+            _say('Found %u images at: %s' % (len(paths), tdir))
             return paths
-    print('ERROR: no image files for grouping found at: %s' % out_dir)
+    _say('ERROR: no image files for grouping found at: %s' % out_dir)
     return None

@@ -25,3 +25,16 @@ def reset_engine(engine=None):
     """Install (tests: a stand-in) or drop the process-wide engine."""
     global _engine
     _engine = engine
+
+
+def is_main():
+    """True on the rank that owns the side effects of the drop-in entry points (files, logs, console).  With one
+    process (the reference's only mode) that is always the caller; under torchrun every rank computes its shard and
+    rank 0 alone touches the file system ('several GPUs')."""
+    return get_engine().comm.rank == 0
+
+
+def sync():
+    """Barrier over the ranks of the engine's group (no-op for one process): the entry points return only after
+    rank 0 has finished moving files, so a caller on any rank sees the final tree."""
+    get_engine().comm.barrier()

@@ -47,6 +47,16 @@ def eval_case(exclude_other):
     return X, (np.ascontiguousarray(R[:4]) if exclude_other else R), ids + 1
 
 
+def classify_faces_case():
+    """(X, R, class names) of the classify_faces / classification-mode golden cases (oracle/make_golden.py:
+    classify_faces_cases): five overlapping blobs, reference embeddings = jittered blob centres, so that some rows fall
+    to a wrong class and some beyond the 'other' threshold."""
+    C, _ = blob_truth(300, 512, kc=5, seed=6)
+    X = blobs(300, 512, kc=5, noise=3.0, seed=6)
+    R = (C + np.float32(0.1) * np.random.default_rng(3).standard_normal(C.shape, dtype=np.float32)).astype(np.float32)
+    return X, R, ['anna', 'bob', 'carol', 'dave', 'eve']
+
+
 def plant_dupes(X, frac=50, seed=1, normalize=True):
     """Plant m = N/frac near-duplicates: sources in rows < N/2, targets in rows >= N/2.
 
@@ -68,6 +78,44 @@ def plant_dupes(X, frac=50, seed=1, normalize=True):
         Y = _normalize_rows(Y)
     X[dst] = Y
     return X, src, dst
+
+
+def adversarial(kind, N=8192, d=512, seed=0):
+    """Inputs built to stress the fp16-operand silhouette sweep ('what's weak' item 2) -- the shapes the
+    application really produces (consecutive frames of one face, `--enc-dup-thr -1`) rather than well-separated blobs:
+
+      'dupes'    30 % of the rows are exact copies: half of them single twins of random rows, half long runs of one
+                 frame (a handful of rows repeated hundreds of times)
+      'tight'    clusters whose spread is 1 % of their separation (intra / inter = 1e-2), not normalised
+      'close'    two of the clusters are 20x closer to each other than to the rest: a and b of their rows are both
+                 small against the (centred) norms, which is where cancellation in |x|^2+|y|^2-2xy hurts
+      'outlier'  one row with 1e4 times the typical norm (forces the power-of-two fp16 scale down for everyone)
+      'offset'   un-centred ViT-like rows: a common offset 50x the spread in every component
+    """
+    rng = np.random.default_rng(1000 + seed)
+    if kind == 'dupes':
+        X = blobs(N, d, kc=6, noise=1.0, seed=seed)
+        n_twin, n_run = int(0.15 * N), int(0.15 * N)
+        dst = rng.choice(N, size=n_twin + n_run, replace=False)
+        src_pool = np.setdiff1d(np.arange(N), dst)
+        X[dst[:n_twin]] = X[rng.choice(src_pool, size=n_twin, replace=True)]
+        runs = rng.choice(src_pool, size=8, replace=False)
+        X[dst[n_twin:]] = X[runs[rng.integers(0, 8, n_run)]]
+        return np.ascontiguousarray(X)
+    if kind == 'tight':
+        return blobs(N, d, kc=6, noise=0.01, seed=seed, normalize=False)
+    if kind == 'close':
+        C = rng.standard_normal((4, d)).astype(np.float32)
+        C[1] = C[0] + np.float32(0.05) * rng.standard_normal(d).astype(np.float32)
+        X = C[rng.integers(0, 4, N)] + np.float32(0.02) * rng.standard_normal((N, d), dtype=np.float32)
+        return np.ascontiguousarray(X, dtype=np.float32)
+    if kind == 'outlier':
+        X = blobs(N, d, kc=6, noise=1.0, seed=seed)
+        X[N // 3] *= np.float32(1e4)
+        return X
+    if kind == 'offset':
+        return np.ascontiguousarray(blobs(N, d, kc=6, noise=1.0, seed=seed, normalize=False) + np.float32(50.0))
+    raise ValueError(kind)
 
 
 def config(name):
