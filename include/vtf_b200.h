@@ -178,6 +178,17 @@ int vtf_wide_update(const int64_t* acc, double inv_two_s, const int64_t* counts,
                     const int32_t* k_off_h, uint32_t active, int d, const float* C_old, float* C_new, double* stats,
                     int stats_stride, void* stream);
 
+/* The same from-scratch sums for NARROW k-ranges (k = 2..6), organised by cells: rows that share their label tuple over
+ * the active labellings are grouped inside each 1024-row chunk (shared-memory counting sort), summed in registers -- one
+ * add per element instead of one read-modify-write per element and labelling -- and folded into the per-cluster sums once
+ * per cell.  acc[slot, j] = sum round(x_j * two_s) for the slots of the ACTIVE labellings (zeroed here; frozen ones keep
+ * their values), bit-identical to vtf_wide_sums_full.  Active labellings are processed in groups of at most 8 with at
+ * most 1024 label tuples and 48 cluster slots; k <= 48 per labelling.  *bad (nullable) = labels outside [0, k).
+ * ws: 64 bytes (chunk counters).  Replaces SK/cluster/_k_means_lloyd.pyx:215-218 behind grouping.py:100.          */
+int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
+                  const int32_t* k_off_h, uint32_t active, double two_s, int64_t* acc, uint32_t* bad, void* ws,
+                  void* stream);
+
 /* ---- a3: nearest-reference classification (grouping.py:51-56) -----------------------------
  * Xn, Rn are cosine-normalised.  dist[N,R] = clip(1 - Xn.Rn^T, 0, 2) (fp32, kept for the
  * '%.4f' log, grouping.py:63); label[i] = argmin (first index), or R when
@@ -238,6 +249,15 @@ int vtf_row_sqnorms(const float* X, int64_t N, int d, float* sqnorm, void* strea
  * (nullable) receives m (-pad_m for padding rows).  P % 256 == 0, d % 64 == 0.                       */
 int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t P, float scale,
                  int shift, float pad_m, void* Xh, void* aug, float* half_sqn, void* stream);
+/* diag: out[p] = out_scale * T_pp for every row, T exactly as the sweeps accumulate it (same MMA shape and order, the
+ * augmented block last).  With an all-zero `aug` this is the squared norm of row p of Xh IN THE TENSOR CORE'S ARITHMETIC
+ * (truncating fp32 accumulation); out_scale = 0.5 gives the half squared norms m.  aug (below) builds the augmented
+ * operand from such m[P] (perm[p] < 0, or p >= N without perm = padding row: all-zero block).  Norms from here make T_pq = g_pq - m_p - m_q
+ * cancel when rows p and q coincide and take the accumulation bias out of every small distance -- with the fp32-FMA norms
+ * of vtf_sil_pack that bias is a floor of ~2e-3 |x| (duplicate frames, tight clusters).  With the final aug,
+ * vtf_sil_diag(out_scale = 1) returns the residual T_pp the sweep would see for a duplicate pair (0 when exact).       */
+int vtf_sil_diag(const void* Xh, const void* aug, int64_t P, int d, float out_scale, float* out, void* stream);
+int vtf_sil_aug(const float* m, const int64_t* perm, int64_t N, int64_t P, int shift, void* aug, void* stream);
 /* out[0] = max |x| (picks the power-of-two fp16 scale).                                     */
 int vtf_absmax(const float* X, int64_t N, int d, float* out, void* stream);
 /* sweep: cellsum[g, p] += sum_{q in cell g} sqrt(max(2 (m_p + m_q - xh_p.xh_q), 0)) / scale

@@ -398,6 +398,16 @@ class FakeKernels:
                 lo, hi = int(k_off[L]), int(k_off[L + 1])
                 acc[lo:hi] = torch.zeros((hi - lo, q.shape[1]), dtype=torch.int64).index_add_(0, labels_all[L, b:b + n].to(torch.int64), q)
 
+    CELL_MAX_K = 48
+
+    def cell_sums(self, Xs, labels_all, b, k_off, active, two_s, acc):
+        q = self._fixed(Xs, two_s)
+        n = Xs.shape[0]
+        for L in range(len(k_off) - 1):
+            if (active >> L) & 1:
+                lo, hi = int(k_off[L]), int(k_off[L + 1])
+                acc[lo:hi] = torch.zeros((hi - lo, q.shape[1]), dtype=torch.int64).index_add_(0, labels_all[L, b:b + n].to(torch.int64), q)
+
     def wide_update(self, acc, inv_two_s, counts, changed, k_off, active, C_old, stats_stride):
         sums = acc.to(torch.float64) * inv_two_s
         C_new, _, stats = self.lloyd_update_multi(sums, counts, changed, k_off, active, C_old, stats_stride)

@@ -59,3 +59,31 @@ def test_symmetric_sweep_vs_oracle_real_labels_20k(engine):
         assert np.array_equal(r.seeds, RC.kmeanspp_indices(X, k, 0))          # k-means++ seeds equal sklearn's
         assert abs(rsc[1]) > 1e-3
         np.testing.assert_allclose(sc[1:], rsc[1:], rtol=RTOL, atol=0)
+
+
+def test_duplicate_rows_cancel_in_the_sweep(engine):
+    """The augmented operand carries the tensor core's OWN squared norms (vtf_sil_diag), so T_pq = g_pq - m_p - m_q of two
+    identical rows is whatever T_pp is: report it (0 = exact cancellation) against the old fp32-FMA norms, whose T_pp shows the
+    accumulation bias (~3e-6 m) that sat under every small distance."""
+    K = engine.K
+    X = adversarial('dupes', 8192, 512)
+    ctx = engine.prepare(X)
+    lab = torch.zeros(8192, dtype=torch.int32, device='cuda')
+    perm, chunk_cell, c2c, G, P = engine.build_cells([lab], [1])
+    Xc = engine._pad16(ctx.Xc, 64)
+    scale, shift, pad_m = engine.sil_scale(Xc)
+    out = {}
+    for tc_norms in (False, True):
+        K.tc_norms = tc_norms
+        try:
+            Xh, aug = K.sil_pack(Xc, perm, P, scale, shift, pad_m)
+        finally:
+            K.tc_norms = True
+        m = K.sil_diag(Xh, torch.zeros_like(aug), 0.5)
+        resid = K.sil_diag(Xh, aug, 1.0)
+        live = perm >= 0
+        rel = (resid[live].abs() / m[live]).cpu().numpy()
+        out[tc_norms] = rel
+        print('tc_norms', tc_norms, 'max |T_pp| / m', rel.max(), 'mean', rel.mean(), 'exact zeros', float((rel == 0).mean()))
+    assert out[True].max() <= 2.0 ** -22          # at most a couple of ulps of the norm
+    assert out[True].mean() < 0.1 * out[False].mean()

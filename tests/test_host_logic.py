@@ -302,3 +302,46 @@ def test_wide_lloyd_more_than_32_labellings(eng):
             assert (again == lab).mean() >= 0.995                  # (rows within an ulp of a bisector may flip)
     inert = [r.inertia for r in res]
     assert inert[0] > inert[5] > inert[-1]
+
+
+def test_strict_fits_leave_no_pass_over_X_for_ch_and_db(eng):
+    """A fit that stops on 'labels unchanged' has its per-cluster sums (last M-step) and its distances to the centres
+    (inertia pass) already: CH / DB of such fits take no further pass over X and equal the two-pass form."""
+    X = blobs(3000, 512, kc=6, noise=0.7, seed=4)
+    ks = [2, 3, 4, 5, 6]
+    ctx, res = eng.kmeans_sweep(X, ks, 0)
+    assert all(r.strict for r in res)
+    assert all(r.csums is not None and r.disp is not None for r in res)
+    calls = []
+    K = eng.K
+    orig_disp, orig_sums = K.cluster_dispersion_multi, K.cluster_sums_multi
+    K.cluster_dispersion_multi = lambda *a, **k: (calls.append('disp'), orig_disp(*a, **k))[1]
+    K.cluster_sums_multi = lambda *a, **k: (calls.append('sums'), orig_sums(*a, **k))[1]
+    try:
+        labels, counts = [r.labels for r in res], [r.counts for r in res]
+        fast = eng.ch_db_scores_multi(ctx, labels, ks, counts, [r.csums for r in res], [r.disp for r in res])
+        assert calls == []
+        slow = eng.ch_db_scores_multi(ctx, labels, ks, counts)
+        assert calls == ['sums', 'disp']
+        one_pass = eng.ch_db_scores_multi(ctx, labels, ks, counts, [r.csums for r in res])      # sums reused, distances recomputed
+        assert calls == ['sums', 'disp', 'disp']
+    finally:
+        K.cluster_dispersion_multi, K.cluster_sums_multi = orig_disp, orig_sums
+    np.testing.assert_allclose(np.asarray(fast), np.asarray(one_pass), rtol=1e-11)   # fp32(mean) vs mean: second order
+    np.testing.assert_allclose(np.asarray(fast), np.asarray(slow), rtol=1e-7)        # centred fp32 copy vs the raw rows
+    ref = [RC.cluster_scores(X, r.labels.numpy())[1:] for r in res]
+    np.testing.assert_allclose(np.asarray(fast), np.asarray(ref), rtol=1e-5)
+
+
+def test_cell_sums_are_the_exact_fixed_point_sums(eng):
+    """The M-step of the lock-step loop runs on exact 64-bit fixed-point sums: centres equal the fp64-sum path bit for bit
+    on this input, and a labelling fitted alone equals the same labelling fitted next to the others."""
+    X = blobs(1500, 128, kc=5, noise=1.0, seed=2)
+    ks = [2, 3, 5]
+    ctx, a = eng.kmeans_sweep(X, ks, 0)
+    eng.lockstep = False
+    _, bb = eng.kmeans_sweep(X, ks, 0, ctx=ctx)
+    eng.lockstep = True
+    for ra, rb in zip(a, bb):
+        assert torch.equal(ra.labels, rb.labels) and torch.equal(ra.centers, rb.centers) and ra.n_iter == rb.n_iter
+        assert ra.inertia == rb.inertia

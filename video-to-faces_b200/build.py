@@ -16,8 +16,6 @@ OUT_DIR = osp.join(HERE, 'videotofaces_b200', '_lib')
 LIB = osp.join(OUT_DIR, 'libvtf_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-Xptxas', '-v']
-FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
 

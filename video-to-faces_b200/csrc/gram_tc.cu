@@ -68,6 +68,11 @@ struct Params {
     unsigned int* work_counter;
     long long n_items;
     unsigned long long* tiles_done;   // nullable: += number of 256 x 256 tiles this launch computed
+    // DIAGONAL pass (full-sweep form only): every unit computes just its own diagonal tile and the epilogue stores
+    // diag_out[p] = diag_scale * T_pp instead of distances.  With an all-zero augmented operand T = Xh.Xh^T, so this yields
+    // the squared norms AS THE TENSOR CORE COMPUTES THEM (same instruction shape, same accumulation order as in the sweep).
+    float* diag_out;
+    float diag_scale;
 };
 
 // Work list shared by the three warp roles (they must walk it identically).  `w` = index of the work item.
@@ -107,6 +112,7 @@ __device__ __forceinline__ bool next_work(const Params& prm, int64_t w, int64_t&
     const int seg = (int)(item % prm.n_seg);
     t0 = seg * prm.tiles_per_seg;
     t1 = min(prm.n_tiles, t0 + prm.tiles_per_seg);
+    if (prm.diag_out) { t0 = (int)((prm.rb_begin + (PAIR ? 2 : 1) * rbu) * BM / BN); t1 = t0 + 1; }   // the tile that holds the unit's diagonal
     return true;
 }
 
@@ -333,6 +339,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int kSliceCols = BN / kSlices;
         constexpr bool FRAG = SYM && (VTF_EPI_FRAG != 0);
         const int g = lane >> 2, tq = lane & 3;
+        const bool diag = !SYM && prm.diag_out != nullptr;   // diagonal pass: store T_pp, no cells, no distances
         int as = 0;
         uint32_t acc_ph = 0;
         int64_t w = 0;
@@ -394,9 +401,9 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         VTF_TMEM_LD32(taddr, v);
                     }
 #if VTF_CELL_PREFETCH
-                    const int cell = cells[c];
+                    const int cell = diag ? 0 : cells[c];
 #else
-                    const int cell = __ldg(prm.chunk_cell + (col0 >> 5));
+                    const int cell = diag ? 0 : __ldg(prm.chunk_cell + (col0 >> 5));
 #endif
                     if (cell != cur_cell) {
                         if (cur_cell >= 0) flush_rows(cur_cell);
@@ -459,6 +466,15 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                       cs[0] * prm.flush_scale);
                         }
                     } else {
+                        if (diag) {                              // diagonal pass: store T_pp, no distances (warp-uniform branch)
+                            if (col0 == rowbase) {
+                                float dv = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) dv = (j == lane) ? __uint_as_float(v[j]) : dv;
+                                prm.diag_out[p] = dv * prm.diag_scale;
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = sqrt_approx(fmaxf(-__uint_as_float(v[j]), 0.f));
                         if (col0 == rowbase) {   // the chunk that holds the diagonal: D_pp = 0 (SK/metrics/pairwise.py:2285)
@@ -491,7 +507,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (lane == 0) { if (PAIR) mbar_arrive_remote<SYM>(tempty_bar(as), 0u); else mbar_arrive(tempty_bar(as)); }
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
-            if (cur_cell >= 0) flush_rows(cur_cell);
+            if (cur_cell >= 0 && !diag) flush_rows(cur_cell);
         }
     }
 
@@ -589,6 +605,7 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = 0; prm.sym_world = 1;
     prm.work_counter = nullptr; prm.n_items = 0; prm.tiles_done = nullptr; prm.chunk_tiles = 0;
+    prm.diag_out = nullptr; prm.diag_scale = 0.f;
     const int64_t n_units = units * prm.n_seg;
     if (pair) {
         const int grid = 2 * (int)min(slots, n_units);
@@ -600,6 +617,40 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
     return tc::launch<false, 4, false, false>(ma, mb, maa, mab, prm, grid, stream);
 }
 
+
+// Diagonal pass: out[p] = out_scale * T_pp for every row, T as the sweeps compute it (CTA pairs, M = 256, N = 256, K = 16,
+// k-blocks in order, the augmented block last).  With an all-zero `aug`, T_pp = (Xh.Xh^T)_pp: the squared norm of row p in
+// the TENSOR CORE's arithmetic -- fp32 accumulation with truncation after every MMA, ~3e-6 low after 32 steps.  Norms taken
+// from here make T_pq = g_pq - g_pp/2 - g_qq/2 cancel bit for bit when rows p and q coincide and remove the common bias for
+// rows that nearly do; with fp32-FMA norms (vtf_sil_pack) that bias is a floor of ~2e-3 |x| under every small distance.
+// P/256 tiles = P * 256 * 2 * d flop: 0.03 % of a sweep.
+extern "C" int vtf_sil_diag(const void* Xh, const void* aug, int64_t P, int d, float out_scale, float* out, void* stream) {
+    VTF_REQUIRE(Xh && aug && out && P > 0 && P % tc::BN == 0 && d >= 64 && d <= 1024 && d % 64 == 0, "vtf_sil_diag");
+    int rc = vtf_device_check();
+    if (rc != VTF_OK) return rc;
+    CUtensorMap ma, mb, maa, mab;
+    if ((rc = tc::make_operand_map(&ma, Xh, P, d, tc::BM, "vtf_sil_diag")) != VTF_OK) return rc;
+    if ((rc = tc::make_operand_map(&mb, Xh, P, d, tc::BN / 2, "vtf_sil_diag")) != VTF_OK) return rc;
+    const __half* augA = (const __half*)aug;
+    const __half* augB = augA + (size_t)P * 16;
+    if ((rc = tc::make_aug_map(&maa, augA, P, tc::BM / 8)) != VTF_OK) return rc;
+    if ((rc = tc::make_aug_map(&mab, augB, P, (tc::BN / 2) / 8)) != VTF_OK) return rc;
+    tc::Params prm;
+    prm.chunk_cell = (const int32_t*)out;           // not read in this mode (the cell look-up of the epilogue needs a valid address)
+    prm.cellsum = out; prm.P = P;
+    prm.rb_begin = 0; prm.n_rb = P / tc::BM;
+    prm.n_kb = d / tc::BK;
+    prm.n_tiles = (int)(P / tc::BN);
+    prm.n_seg = 1; prm.tiles_per_seg = prm.n_tiles;
+    prm.flush_scale = 0.f;
+    prm.sym_rank = 0; prm.sym_world = 1;
+    prm.work_counter = nullptr; prm.n_items = 0; prm.tiles_done = nullptr; prm.chunk_tiles = 0;
+    prm.diag_out = out; prm.diag_scale = out_scale;
+    const int64_t units = prm.n_rb / 2;
+    const int grid = 2 * (int)min((int64_t)(num_sms() / 2), units);
+    if (d <= 512) return tc::launch<true, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
+    return tc::launch<false, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
+}
 
 // Symmetric form: D_pq = D_qp, so only tiles on or above the diagonal are computed (half the MMAs, half the L2
 // traffic); every off-diagonal 32 x 32 block also feeds the row sums of its COLUMNS through a warp
@@ -631,6 +682,7 @@ extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = rank; prm.sym_world = world;
     prm.work_counter = work_counter; prm.n_items = 0; prm.tiles_done = (unsigned long long*)tiles_done;
+    prm.diag_out = nullptr; prm.diag_scale = 0.f;
     const int64_t U = prm.n_rb / 2;
     // column chunk: <= 32 MB of B operand (a quarter of the 126 MB L2, so the chunk being left and the one being
     // entered both stay resident), 16..256 tiles; VTF_SWEEP_CHUNK overrides.  Same-box A/B at 1M x 512 (static /

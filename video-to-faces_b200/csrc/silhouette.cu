@@ -81,6 +81,23 @@ __global__ void __launch_bounds__(256) sil_pack_kernel(const float* __restrict__
     }
 }
 
+// Augmented operand from given half squared norms m[p] (vtf_sil_diag: the tensor core's own |Xh_p|^2 / 2); rows with
+// perm[p] < 0 (padding) get the all-zero block.
+__global__ void __launch_bounds__(256) sil_aug_kernel(const float* __restrict__ m, const int64_t* __restrict__ perm, int64_t N, int64_t P,
+                                                      float inv_pow, float cpow, __half* __restrict__ augA, __half* __restrict__ augB) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    if (perm ? perm[p] < 0 : p >= N) {
+        const size_t off = (size_t)(p >> 3) * 128 + (size_t)(p & 7) * 8;
+        *reinterpret_cast<uint4*>(augA + off) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(augB + off) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(augA + off + 64) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(augB + off + 64) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    store_aug(augA, augB, p, m[p] * inv_pow, cpow);
+}
+
 __global__ void __launch_bounds__(256) absmax_kernel(const float4* __restrict__ X, int64_t nvec, unsigned int* __restrict__ out) {
     float m = 0.f;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,6 +216,17 @@ int vtf_sil_pack(const float* X, int64_t N, int d, const int64_t* perm, int64_t 
     VTF_LAUNCH(sil_pack_kernel, grid, 256, 0, stream, X, N, d, perm, P, scale, 1.f / cpow, cpow, pad_m, (__half*)Xh, augA,
                augB, half_sqn);
     VTF_CHECK_LAST("vtf_sil_pack");
+    return VTF_OK;
+}
+
+int vtf_sil_aug(const float* m, const int64_t* perm, int64_t N, int64_t P, int shift, void* aug, void* stream) {
+    VTF_REQUIRE(m && aug && N >= 0 && P >= 0 && P % 8 == 0 && shift >= 0 && shift <= 15, "vtf_sil_aug");
+    if (P == 0) return VTF_OK;
+    const float cpow = (float)(1 << shift);
+    __half* augA = (__half*)aug;
+    __half* augB = augA + (size_t)P * 16;
+    VTF_LAUNCH(sil_aug_kernel, (unsigned)((P + 255) / 256), 256, 0, stream, m, perm, N, P, 1.f / cpow, cpow, augA, augB);
+    VTF_CHECK_LAST("vtf_sil_aug");
     return VTF_OK;
 }
 

@@ -50,6 +50,7 @@ SIGNATURES = {
                                    ctypes.c_double, c_vp, c_vp, c_vp]),
     'vtf_wide_update': (c_int, [c_vp, ctypes.c_double, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_int,
                                 c_vp]),
+    'vtf_cell_sums': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, ctypes.c_double, c_vp, c_vp, c_vp, c_vp]),
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
@@ -62,6 +63,8 @@ SIGNATURES = {
     'vtf_silhouette_rowsums_exact': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     'vtf_row_sqnorms': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_sil_pack': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_sil_diag': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp]),
+    'vtf_sil_aug': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     'vtf_absmax': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_sil_sweep': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     'vtf_sil_sweep_sym': (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

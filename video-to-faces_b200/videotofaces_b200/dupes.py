@@ -25,6 +25,20 @@ def _write_dupes_log(path, filenames, mins, inds, is_dup, measure_name):
             f.write('%s,%s,%s,%s\n' % (filenames[i], filenames[inds[i]], str(mins[i]), '1' if is_dup[i] else '0'))
 
 
+def dedup_rows(X, threshold):
+    """The arithmetic of remove_dupes_overall's 'enc' branch (dupes.py:60-68) without file system effects: returns
+    dict(kept [N - n_dup, d] (numpy for a host X, a CUDA tensor for a device X), idx int64 [n_dup], mins fp32 [N],
+    inds int64 [N])."""
+    eng = get_engine()
+    mins, inds, idx = eng.dedup(X, threshold)                                  # dupes.py:60-65
+    on_device = hasattr(X, 'is_cuda') and X.is_cuda                            # encoder output still on the GPU (section 8f item 2)
+    if on_device:
+        kept = eng.delete_rows(X, idx) if idx.size else X.clone()              # stays in HBM for the grouping that follows
+    else:
+        kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
+    return dict(kept=kept, idx=idx, mins=mins, inds=inds)
+
+
 def remove_dupes_overall(X, filenames, dup_params):
     """Returns (X_kept float32 [N - n_dup, d], goods) exactly like dupes.py:51-92."""
     measure_type, threshold, save_dupes, out_dir = dup_params
@@ -34,18 +48,16 @@ def remove_dupes_overall(X, filenames, dup_params):
     if is_hash:
         mins, inds, idx = eng.dedup_hash(X, threshold)                         # dupes.py:55-58, 62-65
     else:
-        mins, inds, idx = eng.dedup(X, threshold)                              # dupes.py:60-65
+        r = dedup_rows(X, threshold)                                           # dupes.py:60-65, 68
+        mins, inds, idx = r['mins'], r['inds'], r['idx']
     is_dup = np.zeros(n, dtype=bool)
     is_dup[idx] = True
     dupes = [fn for i, fn in enumerate(filenames) if is_dup[i]]                # dupes.py:66-67
     goods = [fn for i, fn in enumerate(filenames) if not is_dup[i]]
-    on_device = hasattr(X, 'is_cuda') and X.is_cuda                            # encoder output still on the GPU (section 8f item 2)
     if is_hash:
         X_kept = np.delete(np.asarray(X), idx, axis=0)                         # 64 ints per row: host bookkeeping
-    elif on_device:
-        X_kept = eng.delete_rows(X, idx) if idx.size else X.clone()            # stays in HBM for the grouping that follows
     else:
-        X_kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
+        X_kept = r['kept']
 
     face_dir = osp.join(out_dir, 'faces')
     if not is_main():                                                          # several ranks: rank 0 owns files, logs and console

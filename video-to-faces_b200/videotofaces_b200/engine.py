@@ -31,7 +31,7 @@ SOLO_ROWS_PER_RANK = 64   # fewer rows per rank than this: no sharding, every ra
 
 
 class KMeansResult:
-    __slots__ = ('k', 'labels', 'centers', 'inertia', 'n_iter', 'seeds', 'counts', 'strict', 'csums')
+    __slots__ = ('k', 'labels', 'centers', 'inertia', 'n_iter', 'seeds', 'counts', 'strict', 'csums', 'disp')
 
     def __init__(self, **kw):
         for n in self.__slots__:
@@ -40,7 +40,7 @@ class KMeansResult:
 
 class FitContext:
     """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
-    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide')
+    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide', 'amax', 'max_sqn')
 
 
 def n_local_trials(k):
@@ -181,7 +181,8 @@ class GroupingEngine:
             raise ValueError('tensor-core dedup needs d <= 4096')
         X = self._pad16(X, 64 if use_tc else 16)
         d = X.shape[1]
-        Xn = self.K.normalize_rows(X)
+        with self.span('normalize'):
+            Xn = self.K.normalize_rows(X)
         with self.span('dedup', flops=float(N) * N * d):
             key = (self.K.cosine_dedup_tc if use_tc else self.K.cosine_dedup)(Xn, self.comm.rank, self.comm.world)
         self.comm.allreduce_min(key)
@@ -215,7 +216,9 @@ class GroupingEngine:
         keep = np.ones(X.shape[0], dtype=bool)
         keep[idx] = False
         kept = torch.from_numpy(np.nonzero(keep)[0].astype(np.int64)).to(self.device)
-        return self.K.gather_rows(self._pad16(X), kept)[:, :d].contiguous()
+        with self.span('delete_rows'):
+            out = self.K.gather_rows(self._pad16(X), kept)
+        return out if out.shape[1] == d else out[:, :d].contiguous()
 
     # ------------------------------------------------------------------------------ a3 classify
     def classify(self, X, R, thr):
@@ -232,14 +235,16 @@ class GroupingEngine:
         return dist, label
 
     def _classify(self, X, R, thr):
-        Xn = self.K.normalize_rows(X)
-        Rn = self.K.normalize_rows(R)
+        with self.span('normalize'):
+            Xn = self.K.normalize_rows(X)
+            Rn = self.K.normalize_rows(R)
         b, e = self._my_rows(X.shape[0])
         on = bool(thr) and thr != -1 and thr >= 0
         nR = R.shape[0]
         dist = self.K.zeros((X.shape[0], nR), torch.float32) if self.comm.active else None
         label = self.K.zeros((X.shape[0],), torch.int64) if self.comm.active else None
-        d_loc, l_loc = self.K.cosine_classify(Xn[b:e], Rn, float(thr) if on else -1.0)
+        with self.span('classify'):
+            d_loc, l_loc = self.K.cosine_classify(Xn[b:e], Rn, float(thr) if on else -1.0)
         if self.comm.active:
             dist[b:e] = d_loc
             label[b:e] = l_loc
@@ -317,55 +322,20 @@ class GroupingEngine:
 
     # ------------------------------------------------------------------------------ a6 Lloyd
     def lloyd(self, ctx, C0, max_iter=300):
-        """SK/cluster/_kmeans.py:629-758 (single Lloyd run) from centred initial centres C0 [k,d]."""
-        K, comm = self.K, self.comm
-        N, d, b, e = ctx.N, ctx.d, ctx.b, ctx.e
-        k = C0.shape[0]
-        C = C0.contiguous().clone()
-        labels = torch.full((N,), -1, dtype=torch.int32, device=self.device)
-        Xs, ls = ctx.Xc[b:e], labels[b:e]
-        red = K.zeros((k * d + k + 1,), torch.float64)
-        strict = False
-        n_iter = 0
-        C64 = None
-        counts = None
-        for it in range(max_iter):
-            counts = K.zeros((k,), torch.int64)
-            n_changed = K.zeros((1,), torch.int64)
-            K.lloyd_assign(Xs, C, ls, counts, n_changed)
-            sums = K.cluster_sums(Xs, ls, k)
-            if comm.active:
-                red[:k * d] = sums.view(-1)
-                red[k * d:k * d + k] = counts.to(torch.float64)
-                red[k * d + k] = n_changed[0].to(torch.float64)
-                comm.allreduce_sum(red)
-                sums = red[:k * d].view(k, d).clone()
-                counts = red[k * d:k * d + k].round().to(torch.int64)
-                n_changed = red[k * d + k:].round().to(torch.int64)
-            C_new, C64, stats = K.lloyd_update(sums, counts, n_changed, C)
-            st = stats.cpu().numpy()                                           # the one D2H of the iteration
-            if (st[2:] == 0).any():
-                C_new, C64, st = self._relocate_empty(ctx, labels, C, sums, counts, n_changed, st)
-            C = C_new                                                          # _kmeans.py:721
-            n_iter = it + 1
-            if st[1] == 0:                                                     # labels == labels_old, :723
-                strict = True
-                break
-            if st[0] <= ctx.tol:                                               # :731-738
-                break
-        if not strict:                                                         # :742-754
-            counts = K.zeros((k,), torch.int64)
-            n_changed = K.zeros((1,), torch.int64)
-            K.lloyd_assign(Xs, C, ls, counts, n_changed)
-            comm.allreduce_sum(counts)
-            C64 = C.to(torch.float64)
-        sq, _, _ = K.cluster_dispersion(Xs, ls, C64)                           # _k_means_common.pyx:94-124
-        comm.allreduce_sum(sq)
-        comm.allgather_rows(labels, ctx.bounds)
-        inertia = float(sq.sum().item())
-        centers = (C + ctx.mean32)[:, :ctx.d_orig].contiguous()                # _kmeans.py:1543-1546
-        return KMeansResult(k=k, labels=labels, centers=centers, inertia=inertia, n_iter=n_iter,
-                            counts=counts, strict=strict)
+        """SK/cluster/_kmeans.py:629-758 (single Lloyd run) from centred initial centres C0 [k,d]: the lock-step loop
+        with one labelling, so that a fit gives the same bits whether it runs alone or next to the other k."""
+        return self._lloyd_group(ctx, [C0], max_iter)[0]
+
+    def _amax(self, ctx):
+        """max |x| of the centred matrix, once per fit context (fixed-point unit of the M-step sums, fp16 scales)."""
+        if getattr(ctx, 'amax', None) is None:
+            ctx.amax = float(self.K.absmax(ctx.Xc).item())                     # every rank holds the whole matrix
+        return ctx.amax if ctx.amax > 0.0 else 1.0
+
+    def _fixed_point(self, ctx):
+        """(2^S, 2^-S): the unit of the exact 64-bit fixed-point cluster sums, |sum| <= N * max|x| * 2^S < 2^62."""
+        S = 61 - math.ceil(math.log2(max(ctx.N, 2) * self._amax(ctx)))
+        return 2.0 ** S, 2.0 ** -S
 
     @staticmethod
     def _pack_groups(ks, d):
@@ -399,6 +369,9 @@ class GroupingEngine:
         return out
 
     def _lloyd_group(self, ctx, C0s, max_iter):
+        """Lock-step Lloyd for a group of labellings: per iteration ONE E-step pass over X (register-tiled fp32 kernel,
+        all centres of the group) and ONE M-step pass (cell-wise exact fixed-point sums, csrc/cells.cu), then the centre
+        update and the per-labelling stopping rules of SK/cluster/_kmeans.py:700-758."""
         K, comm = self.K, self.comm
         N, d, b, e = ctx.N, ctx.d, ctx.b, ctx.e
         nL = len(C0s)
@@ -409,24 +382,39 @@ class GroupingEngine:
         C_all = torch.cat([c.contiguous() for c in C0s]).contiguous()
         labels_all = torch.full((nL, N), -1, dtype=torch.int32, device=self.device)
         Xs = ctx.Xc[b:e]
+        cells = hasattr(K, 'cell_sums') and max(ks) <= K.CELL_MAX_K and d % 2 == 0
+        if cells:
+            two_s, inv_two_s = self._fixed_point(ctx)
+            acc = K.zeros((ktot, d), torch.int64)
         active = (1 << nL) - 1
-        n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
+        n_iter, strict, counts_fin, csums = [0] * nL, [False] * nL, [None] * nL, [None] * nL
         for it in range(max_iter):
             cc = K.zeros((ktot + nL,), torch.int64)                            # counts | changed: one memset, one all-reduce
             counts, changed = cc[:ktot], cc[ktot:]
             K.lloyd_assign_multi(Xs, C_all, off, active, labels_all, b, counts, changed)
-            sums = K.cluster_sums_multi(Xs, labels_all, b, off, active)
-            comm.allreduce_sum(sums)
-            comm.allreduce_sum(cc)
-            C_new, _, stats = K.lloyd_update_multi(sums, counts, changed, off, active, C_all, stride)
+            if cells:
+                K.cell_sums(Xs, labels_all, b, off, active, two_s, acc)
+                acc_g = acc
+                if comm.active:
+                    acc_g = acc.clone()
+                    comm.allreduce_sum(acc_g)                                  # integers: exact in any order
+                    comm.allreduce_sum(cc)
+                C_new, stats = K.wide_update(acc_g, inv_two_s, counts, changed, off, active, C_all, stride)
+            else:
+                sums = K.cluster_sums_multi(Xs, labels_all, b, off, active)
+                comm.allreduce_sum(sums)
+                comm.allreduce_sum(cc)
+                C_new, _, stats = K.lloyd_update_multi(sums, counts, changed, off, active, C_all, stride)
             st = stats.cpu().numpy()                                           # the one D2H of the iteration
             for L in range(nL):
                 if not (active >> L) & 1:
                     continue
                 lo, hi = int(off[L]), int(off[L + 1])
                 stL = st[L, :2 + hi - lo]
+                sumsL = None
                 if (stL[2:] == 0).any():                                       # empty cluster: relocate (rare)
-                    cn, _, stL = self._relocate_empty(ctx, labels_all[L], C_all[lo:hi].contiguous(), sums[lo:hi].contiguous(),
+                    sumsL = (acc_g[lo:hi].to(torch.float64) * inv_two_s) if cells else sums[lo:hi].contiguous()
+                    cn, _, stL = self._relocate_empty(ctx, labels_all[L], C_all[lo:hi].contiguous(), sumsL,
                                                       counts[lo:hi].contiguous(), changed[L:L + 1].contiguous(), stL)
                     C_new[lo:hi] = cn
                 n_iter[L] = it + 1
@@ -434,6 +422,8 @@ class GroupingEngine:
                     strict[L] = True
                     active &= ~(1 << L)
                     counts_fin[L] = counts[lo:hi].clone()
+                    if sumsL is None:      # the sums of this pass ARE the per-cluster sums of the final labels: CH / DB reuse them
+                        csums[L] = (acc_g[lo:hi].to(torch.float64) * inv_two_s) if cells else sums[lo:hi].clone()
                 elif stL[0] <= ctx.tol:                                        # _kmeans.py:731-738
                     active &= ~(1 << L)
             C_all = C_new                                                      # _kmeans.py:721
@@ -448,8 +438,10 @@ class GroupingEngine:
             for L in range(nL):
                 if not strict[L]:
                     counts_fin[L] = counts[int(off[L]):int(off[L + 1])].clone()
-        sq, _ = K.cluster_dispersion_multi(Xs, labels_all, b, off, (1 << nL) - 1, C_all.to(torch.float64))
-        comm.allreduce_sum(sq)
+        sq, rt = K.cluster_dispersion_multi(Xs, labels_all, b, off, (1 << nL) - 1, C_all.to(torch.float64))
+        both = torch.cat([sq, rt])
+        comm.allreduce_sum(both)
+        sq, rt = both[:ktot], both[ktot:]
         sq_h = sq.cpu().numpy()
         res = []
         for L in range(nL):
@@ -458,7 +450,8 @@ class GroupingEngine:
             comm.allgather_rows(lab, ctx.bounds)
             centers = (C_all[lo:hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()  # _kmeans.py:1543-1546
             res.append(KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
-                                    n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L]))
+                                    n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L], csums=csums[L],
+                                    disp=(sq[lo:hi], rt[lo:hi]) if strict[L] else None))
         return res
 
     # ------------------------------------------------------------------------------ a6, wide k-ranges on the tensor cores
@@ -480,14 +473,13 @@ class GroupingEngine:
             Xs = ctx.Xc[ctx.b:ctx.e]
             n = Xs.shape[0]
             P = ((n + 255) // 256) * 256
-            amax = float(K.absmax(ctx.Xc).item())
-            amax = amax if amax > 0.0 else 1.0
+            amax = self._amax(ctx)
             scale = 2.0 ** min(60, math.floor(math.log2(2048.0 / amax)))   # hi keeps 11 bits, lo the next 11; 1/scale^2 stays a normal fp32
             Xhi, Xlo = K.split_fp16(Xs, P, scale)
             rown = K.zeros((P,), torch.float32)
             rown[:n] = torch.sqrt(K.row_sqnorms(Xs))
-            S = 61 - math.ceil(math.log2(max(ctx.N, 2) * amax))           # |sum| <= N * amax * 2^S < 2^62
-            ctx.wide = dict(Xhi=Xhi, Xlo=Xlo, rown=rown, scale=scale, two_s=2.0 ** S, inv_two_s=2.0 ** -S, n=n)
+            two_s, inv_two_s = self._fixed_point(ctx)
+            ctx.wide = dict(Xhi=Xhi, Xlo=Xlo, rown=rown, scale=scale, two_s=two_s, inv_two_s=inv_two_s, n=n)
         return ctx.wide
 
     @staticmethod
@@ -644,8 +636,10 @@ class GroupingEngine:
             g0, g1 = grp[0], grp[-1] + 1
             lo0, hi0 = int(off[g0]), int(off[g1])
             sub_off = (off[g0:g1 + 1] - off[g0]).astype(np.int32)
-            sq, _ = K.cluster_dispersion_multi(Xs, labels_all[g0:g1], b, sub_off, (1 << (g1 - g0)) - 1, C64_all[lo0:hi0].contiguous())
-            comm.allreduce_sum(sq)
+            sq, rt = K.cluster_dispersion_multi(Xs, labels_all[g0:g1], b, sub_off, (1 << (g1 - g0)) - 1, C64_all[lo0:hi0].contiguous())
+            both = torch.cat([sq, rt])
+            comm.allreduce_sum(both)
+            sq, rt = both[:hi0 - lo0], both[hi0 - lo0:]
             sq_h = sq.cpu().numpy()
             for L in grp:
                 lo, hi = int(off[L]) - lo0, int(off[L + 1]) - lo0
@@ -654,7 +648,7 @@ class GroupingEngine:
                 centers = (C_all[lo0 + lo:lo0 + hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()   # _kmeans.py:1543-1546
                 res[L] = KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
                                       n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L],
-                                      csums=csums[lo0 + lo:lo0 + hi])
+                                      csums=csums[lo0 + lo:lo0 + hi], disp=(sq[lo:hi], rt[lo:hi]) if strict[L] else None)
         return res
 
     def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):
@@ -719,7 +713,7 @@ class GroupingEngine:
         """calinski_harabasz_score and davies_bouldin_score for one labelling (see ch_db_scores_multi)."""
         return self.ch_db_scores_multi(ctx, [labels], [k], [counts])[0]
 
-    def ch_db_scores_multi(self, ctx, labels_list, ks, counts_list=None, csums_list=None):
+    def ch_db_scores_multi(self, ctx, labels_list, ks, counts_list=None, csums_list=None, disp_list=None):
         """calinski_harabasz_score and davies_bouldin_score (SK/metrics/cluster/_unsupervised.py:333-487) for every
         labelling of the k-range with TWO passes over X in total: one for all per-cluster sums, one for all
         distances to the cluster means (the reference makes both passes once per k)."""
@@ -733,13 +727,17 @@ class GroupingEngine:
         # Both scores are translation invariant.  When the fits left their per-cluster sums of the centred rows (the wide Lloyd
         # path keeps them exact and consistent with the final labels) the first pass over X is not needed: work on Xc.
         centred = csums_list is not None and all(c is not None for c in csums_list)
+        # A fit that stopped on 'labels unchanged' (SK/cluster/_kmeans.py:723) has centres = fp32(means of its final labels), and
+        # its inertia pass already measured every row against them: sq = CH's intra dispersion and rt = DB's distance sums up
+        # to the fp32 rounding of the means (a second-order effect, ~1e-14 relative), so NO pass over X is left for the scores.
+        reuse = centred and disp_list is not None and all(dd is not None for dd in disp_list)
         Xsrc = ctx.Xc if centred else ctx.X
         gmean = (ctx.col_sum / ctx.N - ctx.mean32.to(torch.float64)) if centred else ctx.mean64
         for grp in self._pack_groups(ks, 0):
             gk = [ks[j] for j in grp]
             off = np.concatenate([[0], np.cumsum(gk)]).astype(np.int32)
             nL = len(grp)
-            labels_all = torch.stack([labels_list[j] for j in grp]).contiguous()
+            labels_all = None if reuse else torch.stack([labels_list[j] for j in grp]).contiguous()
             full = (1 << nL) - 1
             if centred:
                 sums = torch.cat([csums_list[j] for j in grp]).contiguous()
@@ -748,9 +746,12 @@ class GroupingEngine:
                 comm.allreduce_sum(sums)
             cnt_all = torch.cat([counts_list[j] for j in grp]).to(torch.float64)
             means = (sums / cnt_all.clamp_min(1).unsqueeze(1)).contiguous()
-            sq, rt = K.cluster_dispersion_multi(Xsrc[b:e], labels_all, b, off, full, means)
-            both = torch.cat([sq, rt])
-            comm.allreduce_sum(both)
+            if reuse:
+                both = torch.cat([disp_list[j][0] for j in grp] + [disp_list[j][1] for j in grp])
+            else:
+                sq, rt = K.cluster_dispersion_multi(Xsrc[b:e], labels_all, b, off, full, means)
+                both = torch.cat([sq, rt])
+                comm.allreduce_sum(both)
             ktot = int(off[-1])
             sq_h, rt_h = both[:ktot].cpu().numpy(), both[ktot:].cpu().numpy()
             means_h, cnt_h, mean_h = means.cpu().numpy(), cnt_all.cpu().numpy(), gmean.cpu().numpy()
@@ -990,5 +991,6 @@ class GroupingEngine:
         counts = [r.counts for r in results]
         sil = self.silhouette_scores(ctx, labels, ks, counts, force=force)
         with self.span('ch_db'):
-            chdb = self.ch_db_scores_multi(ctx, labels, ks, counts, [getattr(r, 'csums', None) for r in results])
+            chdb = self.ch_db_scores_multi(ctx, labels, ks, counts, [getattr(r, 'csums', None) for r in results],
+                                           [getattr(r, 'disp', None) for r in results])
         return [(r.k, float(s), ch, db) for r, s, (ch, db) in zip(results, sil, chdb)]

@@ -258,6 +258,18 @@ class CudaKernels:
                 ptr(C_old), ptr(C_new), ptr(stats), c_int(stats_stride), stream())
         return C_new, stats
 
+    # ------------------------------------------------------------------ a6, narrow k-ranges: sums by cells (csrc/cells.cu)
+    CELL_MAX_K = 48                    # clusters per labelling the cell kernel takes
+
+    def cell_sums(self, Xs, labels_all, b, k_off, active, two_s, acc):
+        """acc[slot] = fixed-point sums (round(x * two_s), int64) of the rows of every ACTIVE labelling's clusters; frozen
+        labellings keep theirs.  Same values as wide_sums_full."""
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        ws = self._workspace(64)
+        nv.call('vtf_cell_sums', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
+                c_int(len(k_off) - 1), koff, active, two_s, ptr(acc), None, ptr(ws), stream())
+
     # ------------------------------------------------------------------ a3 / a1
     def cosine_classify(self, Xn, Rn, thr):
         N, d = self._chk(Xn)
@@ -316,14 +328,28 @@ class CudaKernels:
         nv.call('vtf_absmax', ptr(X), c_i64(N), c_int(d), ptr(out), stream())
         return out
 
+    tc_norms = True        # augmented operand from the tensor core's own squared norms (vtf_sil_diag); False: fp32-FMA norms
+
     def sil_pack(self, X, perm, P, scale, shift, pad_m):
-        """fp16 operand [P,d] + augmented norm columns [2,P,16] (A and B flavour) for the tensor-core sweep."""
+        """fp16 operand [P,d] + augmented norm columns [2,P,16] (A and B flavour) for the tensor-core sweep.  The norms
+        that ride in the augmented columns are taken from a diagonal pass of the sweep kernel itself, so that they carry
+        the same accumulation rounding as the Gram entries they are subtracted from."""
         N, d = self._chk(X)
         Xh = self.empty((P, d), torch.float16)
         aug = self.empty((2, P, 16), torch.float16)
         nv.call('vtf_sil_pack', ptr(X), c_i64(N), c_int(d), ptr(perm), c_i64(P), c_f32(scale), c_int(shift), c_f32(pad_m),
                 ptr(Xh), ptr(aug), None, stream())
+        if self.tc_norms and P % 256 == 0 and d % 64 == 0 and 64 <= d <= 1024:
+            m = self.sil_diag(Xh, torch.zeros_like(aug), 0.5)
+            nv.call('vtf_sil_aug', ptr(m), ptr(perm), c_i64(N), c_i64(P), c_int(shift), ptr(aug), stream())
         return Xh, aug
+
+    def sil_diag(self, Xh, aug, out_scale):
+        """out[p] = out_scale * T_pp as the sweep accumulates it (zero aug: the tensor core's squared norms)."""
+        P, d = Xh.shape
+        out = self.empty((P,), torch.float32)
+        nv.call('vtf_sil_diag', ptr(Xh), ptr(aug), c_i64(P), c_int(d), c_f32(out_scale), ptr(out), stream())
+        return out
 
     def sil_sweep(self, Xh, aug, scale, chunk_cell, n_cells, rb_begin, rb_end, cellsum):
         P, d = Xh.shape
