@@ -52,6 +52,11 @@ int vtf_col_stats(const float* X, int64_t N, int d, double* col_sum, double* col
                   void* ws, void* stream);
 /* Xc = X - mean (fp32), SK/cluster/_kmeans.py:1487-1490.                                   */
 int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* Xc, void* stream);
+/* The same, plus in the same pass what the later stages ask of the centred matrix: stats[0] = max |xc| (fp16 scales of the
+ * tensor-core operands, unit of the fixed-point M-step sums), stats[1] = max_row |xc_row|^2 (range of the norm pieces of
+ * the sweep's augmented operand), sqn[N] (nullable) = |xc_row|^2, all fp32.                                   */
+int vtf_center_rows_stats(const float* X, int64_t N, int d, const float* mean, float* Xc, float* sqn, float* stats,
+                          void* stream);
 
 /* ---- a7: k-means++ (SK/cluster/_kmeans.py:180-278) ----------------------------------------
  * kpp_dist: for T candidate centres cand[T,d], out[t,i] = min(closest[i], ||x_i - cand_t||^2)
@@ -188,6 +193,18 @@ int vtf_wide_update(const int64_t* acc, double inv_two_s, const int64_t* counts,
 int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
                   const int32_t* k_off_h, uint32_t active, double two_s, int64_t* acc, uint32_t* bad, void* ws,
                   void* stream);
+
+/* Cell layout of the silhouette sweep on the device (replaces a torch.unique / argsort chain): labels[n_lab][label_stride]
+ * are ALL labellings of the k-range (k_h[q] clusters each, at most 4096 label tuples in total).  Occupied tuples = cells,
+ * numbered g = 0..G-1 in key order (key = sum_q label_q * prod_{q' < q} k_q'); cell g takes ceil32(size) positions, the
+ * total is padded to a multiple of 256.  perm[p] = row at position p (-1: padding), chunk_cell[p/32] = cell of the 32
+ * positions, c2c[q * c2c_stride + g] = cluster of cell g in labelling q, meta = {G, P, positions in use}.  perm_cap >=
+ * ceil256(N + 31 * min(tuples, N)), chunk_cell holds perm_cap/32 entries, c2c_stride >= min(tuples, N).
+ * ws: vtf_build_cells_ws_bytes(N).                                                                           */
+size_t vtf_build_cells_ws_bytes(int64_t N);
+int vtf_build_cells(const int32_t* labels, int64_t label_stride, int64_t N, int n_lab, const int32_t* k_h, int64_t* perm,
+                    int64_t perm_cap, int32_t* chunk_cell, int32_t* c2c, int c2c_stride, int64_t* meta, void* ws,
+                    void* stream);
 
 /* ---- a3: nearest-reference classification (grouping.py:51-56) -----------------------------
  * Xn, Rn are cosine-normalised.  dist[N,R] = clip(1 - Xn.Rn^T, 0, 2) (fp32, kept for the

@@ -369,3 +369,84 @@ def test_sweep_rejects_bad_shapes(K):
     with pytest.raises(_native.NativeError):
         K.sil_sweep(torch.zeros((100, 64), dtype=torch.float16, device='cuda'), torch.zeros((2, 100, 16), dtype=torch.float16, device='cuda'), 1.0,
                     torch.zeros(4, dtype=torch.int32, device='cuda'), 1, 0, 1, torch.zeros((1, 100), device='cuda'))
+
+
+@pytest.mark.parametrize('N,d', [(5, 512), (4097, 512), (3000, 768), (2049, 1024), (100, 36)])
+def test_center_rows_with_stats(K, N, d):
+    """The centring pass that also returns max |xc| and max |xc_row|^2: Xc bit-equal to X - mean, the maxima exact / 1 ulp."""
+    X = blobs(N, d, kc=3, seed=N, normalize=False) + 0.5
+    mean32 = (X.astype(np.float64).sum(0) / N).astype(np.float32)
+    Xc, stats = K.center_rows_stats(dev(X), dev(mean32))
+    want = X - mean32
+    assert np.array_equal(Xc.cpu().numpy(), want)
+    st = stats.cpu().numpy()
+    assert st[0] == np.abs(want).max()
+    np.testing.assert_allclose(st[1], (want.astype(np.float64) ** 2).sum(1).max(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('N,d,ks,active', [
+    (5000, 512, [2, 3, 4, 5, 6], 0b11111),          # one group, 720 label tuples
+    (3000, 768, [2, 3, 4, 5, 6], 0b10110),          # frozen labellings keep their sums; 2 column slices, the second half empty
+    (1025, 1024, [7, 9, 11, 13], 0b1111),           # 9009 tuples: split into groups
+    (777, 64, [48], 0b1),                           # the largest k one labelling may have
+    (2048, 130, [3, 2], 0b11),                      # d not a multiple of 4 * 32
+    (40000, 512, [2, 3, 4, 5, 6, 7, 8, 9, 10], 0b111111111),   # more than 8 labellings
+])
+def test_cell_sums_kernel(K, N, d, ks, active):
+    """Cell-wise fixed-point cluster sums against a plain index_add of round(x * 2^S): integers, so bit-exact."""
+    rng = np.random.default_rng(N)
+    X = (rng.standard_normal((N, d), dtype=np.float32) * 0.3).astype(np.float32)
+    # blob-like labels (few occupied cells) for the first labellings, random ones for the rest
+    base = rng.integers(0, 6, N)
+    labels = np.stack([(base % k if j < 2 else rng.integers(0, k, N)) for j, k in enumerate(ks)]).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    two_s = 2.0 ** 33
+    acc = torch.full((int(off[-1]), d), 12345, dtype=torch.int64, device='cuda')
+    K.cell_sums(dev(X), dev(labels), 0, off, active, two_s, acc)
+    q = torch.from_numpy(np.rint(X.astype(np.float64) * two_s).astype(np.int64))
+    got = acc.cpu()
+    for L, k in enumerate(ks):
+        lo, hi = int(off[L]), int(off[L + 1])
+        if (active >> L) & 1:
+            want = torch.zeros((k, d), dtype=torch.int64).index_add_(0, torch.from_numpy(labels[L].astype(np.int64)), q)
+            assert torch.equal(got[lo:hi], want), (L, k)
+        else:
+            assert bool((got[lo:hi] == 12345).all())            # untouched
+    # a row shard (b > 0) of a wider label matrix, as the ranks of a multi-GPU run call it
+    b = N // 3
+    acc2 = torch.zeros((int(off[-1]), d), dtype=torch.int64, device='cuda')
+    K.cell_sums(dev(X[b:]), dev(labels), b, off, active, two_s, acc2)
+    L = int(np.log2(active & -active))
+    want = torch.zeros((ks[L], d), dtype=torch.int64).index_add_(0, torch.from_numpy(labels[L, b:].astype(np.int64)), q[b:])
+    assert torch.equal(acc2.cpu()[int(off[L]):int(off[L + 1])], want)
+
+
+@pytest.mark.parametrize('N,ks', [(700, [2, 3, 5]), (100_000, [2, 3, 4, 5, 6]), (33, [4]), (5000, [16, 16, 16]), (257, [2, 2])])
+def test_build_cells_kernel(engine, N, ks):
+    """Cell layout on the device: every row once, every 32-position chunk inside one cell, cells in key order and padded to
+    32, P padded to 256, cell -> cluster tables right; same cell count as torch.unique of the label tuples."""
+    K = engine.K
+    rng = np.random.default_rng(N)
+    base = rng.integers(0, 7, N)
+    labels = np.stack([(base * (j + 1) + (rng.random(N) < 0.05)) % k for j, k in enumerate(ks)]).astype(np.int32)
+    perm, chunk_cell, c2c, G, P = K.build_cells(dev(labels), ks)
+    pm, cc, cm = perm.cpu().numpy(), chunk_cell.cpu().numpy(), c2c.cpu().numpy()
+    assert P % 256 == 0 and pm.shape == (P,) and cc.shape == (P // 32,) and cm.shape == (len(ks), G)
+    assert sorted(pm[pm >= 0].tolist()) == list(range(N))
+    assert G == len(np.unique(labels.T, axis=0))
+    cell_of_pos = np.repeat(cc, 32)
+    live = pm >= 0
+    for j in range(len(ks)):
+        assert np.array_equal(cm[j][cell_of_pos[live]], labels[j][pm[live]])
+    # cells are contiguous, in ascending order, each a multiple of 32 positions; padding only at the end of a cell
+    used = cell_of_pos[:np.nonzero(live)[0].max() + 1]
+    assert np.all(np.diff(used) >= 0)
+    sizes = np.bincount(cell_of_pos[live], minlength=G)
+    starts = np.concatenate([[0], np.cumsum((sizes + 31) // 32 * 32)])
+    for g in range(G):
+        seg = pm[starts[g]:starts[g + 1]]
+        assert (seg[:sizes[g]] >= 0).all() and (seg[sizes[g]:] < 0).all()
+    # the engine takes this path for narrow k-ranges and the sort-based one otherwise: same silhouette either way
+    lab_t = [dev(l) for l in labels]
+    p2 = engine.build_cells(lab_t, ks)
+    assert p2[3] == G and p2[4] == P

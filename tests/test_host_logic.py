@@ -345,3 +345,29 @@ def test_cell_sums_are_the_exact_fixed_point_sums(eng):
     for ra, rb in zip(a, bb):
         assert torch.equal(ra.labels, rb.labels) and torch.equal(ra.centers, rb.centers) and ra.n_iter == rb.n_iter
         assert ra.inertia == rb.inertia
+
+
+def test_tolerance_stopped_fits_also_need_no_extra_pass(eng):
+    """A fit that stops on the centre-shift tolerance (SK/cluster/_kmeans.py:731-738) labels the rows once more and its
+    centres are NOT the means of those labels: its final sums come from one more cell-sums pass and it rides through the
+    inertia pass twice (against its centres, against the means).  CH / DB then take no pass of their own either."""
+    X = blobs(8000, 128, kc=8, noise=1.5, seed=3)
+    ks = [2, 3, 4, 5, 6]
+    ctx, res = eng.kmeans_sweep(X, ks, 0)
+    assert [r.strict for r in res] == [True, False, True, True, True]
+    assert all(r.csums is not None and r.disp is not None for r in res)
+    calls = []
+    K = eng.K
+    orig_disp, orig_sums = K.cluster_dispersion_multi, K.cluster_sums_multi
+    K.cluster_dispersion_multi = lambda *a, **k: (calls.append('disp'), orig_disp(*a, **k))[1]
+    K.cluster_sums_multi = lambda *a, **k: (calls.append('sums'), orig_sums(*a, **k))[1]
+    try:
+        scores = eng.cluster_scores(ctx, res, force='exact')
+    finally:
+        K.cluster_dispersion_multi, K.cluster_sums_multi = orig_disp, orig_sums
+    assert calls == []
+    ref = RC.cluster_core(X, ks, 0)
+    for r, lab, inertia, sc, rsc in zip(res, ref['labels'], ref['inertia'], scores, ref['scores']):
+        assert np.array_equal(r.labels.numpy(), lab)
+        np.testing.assert_allclose(r.inertia, inertia, rtol=1e-5)
+        np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-5)

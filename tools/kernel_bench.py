@@ -92,6 +92,13 @@ def main():
     ch_all = torch.zeros(len(ks), dtype=torch.int64, device='cuda')
     add('lloyd_assign_multi k=2..6', lambda: K.lloyd_assign_multi(X, C_all, off, 31, labels_all, 0, cnt_all, ch_all), B + 5 * N * 8, 2.0 * N * 20 * d)
     add('cluster_sums_multi k=2..6', lambda: K.cluster_sums_multi(X, labels_all, 0, off, 31), B + 5 * N * 4)
+    acc = torch.zeros((int(off[-1]), d), dtype=torch.int64, device='cuda')
+    # realistic labellings: nested blobs give 8-20 occupied cells, random labels 720 -- time both
+    add('cell_sums k=2..6 (random labels: 720 cells)', lambda: K.cell_sums(X, labels_all, 0, off, 31, 2.0 ** 30, acc), B + 5 * N * 4)
+    proj = (X[:, :5] > 0).to(torch.int32)
+    labels_blob = torch.stack([(proj[:, :3] * torch.tensor([1, 2, 4], device='cuda', dtype=torch.int32)).sum(1) % kk for kk in ks]).to(torch.int32).contiguous()
+    add('cell_sums k=2..6 (structured labels: <= 8 cells)', lambda: K.cell_sums(X, labels_blob, 0, off, 31, 2.0 ** 30, acc), B + 5 * N * 4)
+    add('cell_sums k=6 alone', lambda: K.cell_sums(X, labels_all, 0, off, 16, 2.0 ** 30, acc), B + N * 4)
     add('cluster_dispersion_multi k=2..6', lambda: K.cluster_dispersion_multi(X, labels_all, 0, off, 31, C_all.double()), B + 5 * N * 4)
     # the same E-step as one tcgen05 contraction (csrc/lloyd_tc.cu): centre pack + split-fp16 assign + exact refine of near ties
     class _Ctx:

@@ -40,13 +40,12 @@ struct CellPlan {
     long long label_stride;
 };
 
-__device__ __forceinline__ float2 ldg_stream2(const float2* p) {
-    float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
+// streaming 8-byte load through the intrinsic (not inline asm): the scheduler knows it is a long-latency load and issues
+// the whole unrolled batch before the first use, PROVIDED the launch bounds tell ptxas that only 2 CTAs fit an SM anyway
+// (shared memory): without the hint it squeezed the kernel into 32 registers and issued the loads two at a time
+__device__ __forceinline__ float2 ldg_stream2(const float2* p) { return __ldcs(p); }
 
-__global__ void __launch_bounds__(kCellThreads) cell_sums_kernel(const float* __restrict__ X, long long n, int d,
+__global__ void __launch_bounds__(kCellThreads, 2) cell_sums_kernel(const float* __restrict__ X, long long n, int d,
                                                                  const int32_t* __restrict__ labels, const CellPlan pl,
                                                                  float two_s, unsigned long long* __restrict__ acc,
                                                                  unsigned int* __restrict__ bad, unsigned int* __restrict__ claim) {
@@ -137,18 +136,20 @@ __global__ void __launch_bounds__(kCellThreads) cell_sums_kernel(const float* __
                 a1 += __float2ll_rn(v[u].y * two_s);
             }
         }
-        if (j < en) {                                               // the tail re-reads the last row (L2 hit) and drops it
-            float2 v[kCellUnroll];
+        for (; j + 4 <= en; j += 4) {                               // tail of the cell in blocks of 4 ...
+            float2 v[4];
 #pragma unroll
-            for (int u = 0; u < kCellUnroll; ++u)
-                v[u] = ldg_stream2(reinterpret_cast<const float2*>(xcol + (size_t)order[min(j + u, en - 1)] * d));
+            for (int u = 0; u < 4; ++u) v[u] = ldg_stream2(reinterpret_cast<const float2*>(xcol + (size_t)order[j + u] * d));
 #pragma unroll
-            for (int u = 0; u < kCellUnroll; ++u) {
-                if (j + u < en) {
-                    a0 += __float2ll_rn(v[u].x * two_s);
-                    a1 += __float2ll_rn(v[u].y * two_s);
-                }
+            for (int u = 0; u < 4; ++u) {
+                a0 += __float2ll_rn(v[u].x * two_s);
+                a1 += __float2ll_rn(v[u].y * two_s);
             }
+        }
+        for (; j < en; ++j) {                                       // ... and single rows
+            const float2 v = ldg_stream2(reinterpret_cast<const float2*>(xcol + (size_t)order[j] * d));
+            a0 += __float2ll_rn(v.x * two_s);
+            a1 += __float2ll_rn(v.y * two_s);
         }
         if (!live) { a0 = 0; a1 = 0; }
         for (int q = 0; q < pl.n_lab; ++q) {
@@ -231,6 +232,176 @@ int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64
                    reinterpret_cast<unsigned long long*>(acc + (size_t)k_off_h[L0] * d), bad, reinterpret_cast<unsigned int*>(ws));
         VTF_CHECK_LAST("vtf_cell_sums");
     }
+    return VTF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cell layout of the silhouette sweep (gram_tc.cu): rows grouped by their joint label tuple over ALL labellings of the
+// k-range, every cell padded to a multiple of 32 positions, the total to a multiple of 256.  Three launches, no sort:
+// keys + histogram, one CTA that numbers the occupied cells (in key order) and lays them out, and the scatter of the row
+// numbers.  Replaces the torch.unique / argsort / cumsum chain (two radix sorts, ~20 launches, three host syncs).
+namespace vtf {
+
+constexpr int kLayoutKeys = 4096;      // joint label tuples the layout kernels can tell apart
+
+struct LayoutPlan {
+    int n_lab;
+    int kk[kMaxSeg];
+    int mult[kMaxSeg];
+    int n_keys;
+    long long label_stride;
+};
+
+__global__ void __launch_bounds__(256) cell_keys_kernel(const int32_t* __restrict__ labels, long long N, const LayoutPlan pl,
+                                                        unsigned short* __restrict__ keys, unsigned int* __restrict__ hist,
+                                                        unsigned int* __restrict__ bad) {
+    __shared__ unsigned int sh[kLayoutKeys];
+    for (int i = threadIdx.x; i < pl.n_keys; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    unsigned int nbad = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+        int key = 0;
+        for (int q = 0; q < pl.n_lab; ++q) {
+            int l = __ldg(labels + (long long)q * pl.label_stride + r);
+            if ((unsigned)l >= (unsigned)pl.kk[q]) { ++nbad; l = 0; }
+            key += l * pl.mult[q];
+        }
+        keys[r] = (unsigned short)key;
+        atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pl.n_keys; i += blockDim.x) { const unsigned int v = sh[i]; if (v) atomicAdd(hist + i, v); }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+// one CTA of 1024 threads, 4 keys per thread: dense cell ids in key order, padded offsets, chunk -> cell table,
+// cell -> cluster tables, meta = {G, P, total}
+__global__ void __launch_bounds__(1024) cell_layout_kernel(const unsigned int* __restrict__ hist, const LayoutPlan pl,
+                                                           int32_t* __restrict__ cell_of_key, unsigned long long* __restrict__ cursor,
+                                                           int32_t* __restrict__ chunk_cell, long long chunk_cap,
+                                                           int32_t* __restrict__ c2c, int c2c_stride, long long* __restrict__ meta) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long s_off[kLayoutKeys + 1];     // padded start of dense cell g
+    __shared__ unsigned long long s_total;
+    __shared__ int s_G;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned int c4[4];
+    unsigned long long local = 0;                                // low 40 bits: padded rows, high bits: occupied cells
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int key = 4 * t + j;
+        c4[j] = key < pl.n_keys ? hist[key] : 0u;
+        if (c4[j]) local += (unsigned long long)((c4[j] + 31u) & ~31u) + (1ull << 40);
+    }
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long base = incl - local;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    if (t == 1023) { s_total = (base + local) & ((1ull << 40) - 1); s_G = (int)((base + local) >> 40); }
+    {
+        unsigned long long pos = base & ((1ull << 40) - 1);
+        int g = (int)(base >> 40);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int key = 4 * t + j;
+            if (key >= pl.n_keys) break;
+            if (c4[j]) {
+                cell_of_key[key] = g;
+                cursor[g] = pos;
+                s_off[g] = pos;
+                for (int q = 0; q < pl.n_lab; ++q) c2c[(size_t)q * c2c_stride + g] = (key / pl.mult[q]) % pl.kk[q];
+                pos += (c4[j] + 31u) & ~31u;
+                ++g;
+            } else {
+                cell_of_key[key] = -1;
+            }
+        }
+    }
+    __syncthreads();
+    const int G = s_G;
+    const unsigned long long total = s_total;
+    if (t == 0) {
+        s_off[G] = total;
+        meta[0] = G;
+        meta[1] = (long long)((total + 255ull) & ~255ull);
+        meta[2] = (long long)total;
+    }
+    __syncthreads();
+    const long long n_chunks = min(chunk_cap, (long long)(((total + 255ull) & ~255ull) / 32ull));
+    for (long long c = t; c < n_chunks; c += 1024) {
+        const unsigned long long pos = (unsigned long long)c * 32ull;
+        int g = 0;
+        if (pos < total) {                                   // binary search: last g with s_off[g] <= pos
+            int lo = 0, hi = G - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= pos) lo = mid; else hi = mid - 1; }
+            g = lo;
+        }
+        chunk_cell[c] = g;                                   // chunks past the last cell (padding to 256 rows): cell 0, zero rows
+    }
+}
+
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const unsigned short* __restrict__ keys, long long N,
+                                                           const int32_t* __restrict__ cell_of_key,
+                                                           unsigned long long* __restrict__ cursor, int64_t* __restrict__ perm) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+        // warp-aggregated claim: lanes of the same cell take consecutive positions with one atomic
+        const int g = cell_of_key[keys[r]];
+        const unsigned int peers = __match_any_sync(__activemask(), g);
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        unsigned long long pos = 0;
+        if (lane == leader) pos = atomicAdd(cursor + g, (unsigned long long)__popc(peers));
+        pos = __shfl_sync(peers, pos, leader) + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
+        perm[pos] = r;
+    }
+}
+
+}  // namespace vtf
+
+extern "C" {
+
+size_t vtf_build_cells_ws_bytes(int64_t N) {
+    return (size_t)N * 2 + 16 + kLayoutKeys * (4 + 4 + 8) + 64;
+}
+
+int vtf_build_cells(const int32_t* labels, int64_t label_stride, int64_t N, int n_lab, const int32_t* k_h, int64_t* perm,
+                    int64_t perm_cap, int32_t* chunk_cell, int32_t* c2c, int c2c_stride, int64_t* meta, void* ws, void* stream) {
+    VTF_REQUIRE(labels && k_h && perm && chunk_cell && c2c && meta && ws && N > 0 && n_lab > 0 && n_lab <= kMaxSeg &&
+                    label_stride >= N && perm_cap % 256 == 0,
+                "vtf_build_cells");
+    LayoutPlan pl = {};
+    long long keys = 1;
+    for (int q = 0; q < n_lab; ++q) {
+        VTF_REQUIRE(k_h[q] > 0, "vtf_build_cells: k > 0");
+        pl.kk[q] = k_h[q];
+        pl.mult[q] = (int)keys;
+        keys *= k_h[q];
+        VTF_REQUIRE(keys <= kLayoutKeys, "vtf_build_cells: more than 4096 label tuples");
+    }
+    pl.n_lab = n_lab; pl.n_keys = (int)keys; pl.label_stride = label_stride;
+    const long long g_max = min((long long)keys, (long long)N);
+    VTF_REQUIRE(perm_cap >= ((N + 31 * g_max + 255) / 256) * 256 && c2c_stride >= g_max, "vtf_build_cells: perm_cap / c2c_stride too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w = (unsigned char*)ws;
+    unsigned int* hist = (unsigned int*)w;                               w += kLayoutKeys * 4;
+    unsigned int* bad = (unsigned int*)w;                                w += 16;
+    int32_t* cell_of_key = (int32_t*)w;                                  w += kLayoutKeys * 4;
+    unsigned long long* cursor = (unsigned long long*)w;                 w += kLayoutKeys * 8;
+    unsigned short* keybuf = (unsigned short*)w;
+    VTF_CUDA(cudaMemsetAsync(hist, 0, kLayoutKeys * 4 + 16, st), "vtf_build_cells/zero");
+    VTF_CUDA(cudaMemsetAsync(perm, 0xff, (size_t)perm_cap * sizeof(int64_t), st), "vtf_build_cells/perm");   // -1 = padding row
+    const int grid = (int)min((int64_t)num_sms() * 8, (N + 255) / 256);
+    VTF_LAUNCH(cell_keys_kernel, grid, 256, 0, stream, labels, (long long)N, pl, keybuf, hist, bad);
+    VTF_CHECK_LAST("vtf_build_cells/keys");
+    VTF_LAUNCH(cell_layout_kernel, 1, 1024, 0, stream, hist, pl, cell_of_key, cursor, chunk_cell, (long long)(perm_cap / 32), c2c,
+               c2c_stride, (long long*)meta);
+    VTF_CHECK_LAST("vtf_build_cells/layout");
+    VTF_LAUNCH(cell_scatter_kernel, grid, 256, 0, stream, keybuf, (long long)N, cell_of_key, cursor, perm);
+    VTF_CHECK_LAST("vtf_build_cells/scatter");
     return VTF_OK;
 }
 

@@ -136,6 +136,61 @@ __global__ void __launch_bounds__(256) center_kernel(const float4* __restrict__ 
     }
 }
 
+// warp per row: Xc = X - mean, plus what the later stages ask of the centred matrix -- max |xc| (fp16 scales, fixed-point
+// unit of the M-step sums) and max |xc_row|^2 (range of the norm pieces in the sweep's augmented operand) -- in the same
+// pass; the row and the lane's slice of the mean stay in registers (DV float4 per lane, d = 128 * DV).
+template <int DV>
+__global__ void __launch_bounds__(256) center_stats_kernel(const float* __restrict__ X, int64_t N, int d, const float* __restrict__ mean,
+                                                           float* __restrict__ Xc, float* __restrict__ sqn,
+                                                           unsigned int* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = d >> 2;
+    float4 mv[DV > 0 ? DV : 1];
+    if (DV > 0) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) mv[v] = __ldg(reinterpret_cast<const float4*>(mean) + lane + 32 * v);
+    }
+    float amax = 0.f, smax = 0.f;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (; row < N; row += stride) {
+        const float4* xr = reinterpret_cast<const float4*>(X + row * d);
+        float4* outr = reinterpret_cast<float4*>(Xc + row * d);
+        float s = 0.f;
+        if (DV > 0) {
+            float4 xv[DV > 0 ? DV : 1];
+#pragma unroll
+            for (int v = 0; v < DV; ++v) xv[v] = ldg_stream(xr + lane + 32 * v);
+#pragma unroll
+            for (int v = 0; v < DV; ++v) {
+                float4 a = xv[v];
+                a.x -= mv[v].x; a.y -= mv[v].y; a.z -= mv[v].z; a.w -= mv[v].w;
+                s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+                outr[lane + 32 * v] = a;
+            }
+        } else {
+            for (int v = lane; v < nvec; v += 32) {
+                float4 a = ldg_stream(xr + v);
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + v);
+                a.x -= m.x; a.y -= m.y; a.z -= m.z; a.w -= m.w;
+                s = fmaf(a.x, a.x, s); s = fmaf(a.y, a.y, s); s = fmaf(a.z, a.z, s); s = fmaf(a.w, a.w, s);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+                outr[v] = a;
+            }
+        }
+        s = warp_sum(s);
+        smax = fmaxf(smax, s);
+        if (sqn && lane == 0) sqn[row] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) {                                   // non-negative floats order like their bit patterns
+        atomicMax(stats + 0, __float_as_uint(amax));
+        atomicMax(stats + 1, __float_as_uint(smax));
+    }
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, int d, const int64_t* __restrict__ idx,
                                                           int64_t n_out, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -209,6 +264,23 @@ int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* 
     int grid = (int)min((int64_t)num_sms() * 16, (nvt + 255) / 256);
     VTF_LAUNCH(center_kernel, grid, 256, 0, stream, (const float4*)X, nvt, d / 4, (const float4*)mean, (float4*)Xc);
     VTF_CHECK_LAST("vtf_center_rows");
+    return VTF_OK;
+}
+
+int vtf_center_rows_stats(const float* X, int64_t N, int d, const float* mean, float* Xc, float* sqn, float* stats,
+                          void* stream) {
+    VTF_REQUIRE(X && Xc && mean && stats && N >= 0 && d > 0 && d % 4 == 0, "vtf_center_rows_stats");
+    VTF_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream), "vtf_center_rows_stats");
+    if (N == 0) return VTF_OK;
+    const int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    const int dv = (d % 128 == 0 && d / 128 <= 8) ? d / 128 : 0;
+#define VTF_CS_CASE(DVv) case DVv: VTF_LAUNCH((center_stats_kernel<DVv>), grid, 256, 0, stream, X, N, d, mean, Xc, sqn, (unsigned int*)stats); break;
+    switch (dv) {
+        VTF_CS_CASE(0) VTF_CS_CASE(1) VTF_CS_CASE(2) VTF_CS_CASE(3) VTF_CS_CASE(4)
+        VTF_CS_CASE(5) VTF_CS_CASE(6) VTF_CS_CASE(7) VTF_CS_CASE(8)
+    }
+#undef VTF_CS_CASE
+    VTF_CHECK_LAST("vtf_center_rows_stats");
     return VTF_OK;
 }
 

@@ -282,8 +282,16 @@ class GroupingEngine:
         ctx.mean64 = s / ctx.N
         ctx.mean32 = ctx.mean64.to(torch.float32)
         var = q / ctx.N - ctx.mean64 * ctx.mean64                              # np.var(X, axis=0), _kmeans.py:292
-        ctx.tol = float(var.clamp_min(0).sum().item()) * 1e-4                  # _kmeans.py:293 (mean taken in prepare())
-        ctx.Xc = self.K.center_rows(X, ctx.mean32)                             # _kmeans.py:1487-1490
+        tol = var.clamp_min(0).sum() * 1e-4                                    # _kmeans.py:293 (mean taken in prepare())
+        if hasattr(self.K, 'center_rows_stats'):
+            # centring pass (_kmeans.py:1487-1490) that also yields max |xc| and max |xc_row|^2; ONE small D2H for the three
+            # scalars the host needs (tolerance, fixed-point unit / fp16 scales, range of the sweep's norm pieces)
+            ctx.Xc, stats = self.K.center_rows_stats(X, ctx.mean32)
+            h = torch.cat([tol.reshape(1), stats.to(torch.float64)]).cpu().numpy()
+            ctx.tol, ctx.amax, ctx.max_sqn = float(h[0]), float(h[1]), float(h[2])
+        else:
+            ctx.tol = float(tol.item())
+            ctx.Xc = self.K.center_rows(X, ctx.mean32)
         return ctx
 
     # ------------------------------------------------------------------------------ a7 k-means++
@@ -438,10 +446,33 @@ class GroupingEngine:
             for L in range(nL):
                 if not strict[L]:
                     counts_fin[L] = counts[int(off[L]):int(off[L + 1])].clone()
-        sq, rt = K.cluster_dispersion_multi(Xs, labels_all, b, off, (1 << nL) - 1, C_all.to(torch.float64))
+            if cells:
+                # the per-cluster sums of the FINAL labels of the tolerance-stopped fits: CH / DB need their means
+                K.cell_sums(Xs, labels_all, b, off, redo, two_s, acc)
+                acc_g = acc
+                if comm.active:
+                    acc_g = acc.clone()
+                    comm.allreduce_sum(acc_g)
+                for L in range(nL):
+                    if not strict[L]:
+                        csums[L] = acc_g[int(off[L]):int(off[L + 1])].to(torch.float64) * inv_two_s
+        # One pass measures every row against the centre of its cluster: sum(sq) is the inertia (_k_means_common.pyx:94-124).
+        # For a fit that stopped on 'labels unchanged' the centres are the fp32 means of its final labels, so the same numbers
+        # are CH's intra dispersion and DB's distance sums; a tolerance-stopped fit rides along a second time, measured
+        # against the fp64 means of its final labels (a "virtual" labelling with the same label row).
+        ext = [L for L in range(nL) if not strict[L] and csums[L] is not None]
+        C64 = C_all.to(torch.float64)
+        labels_x, off_x = labels_all, off
+        if ext:
+            labels_x = torch.cat([labels_all, labels_all[ext]]).contiguous()
+            means = [csums[L] / counts_fin[L].to(torch.float64).clamp_min(1).unsqueeze(1) for L in ext]
+            C64 = torch.cat([C64] + means).contiguous()
+            off_x = np.concatenate([off, off[-1] + np.cumsum([ks[L] for L in ext])]).astype(np.int32)
+        kx = int(off_x[-1])
+        sq, rt = K.cluster_dispersion_multi(Xs, labels_x, b, off_x, (1 << (nL + len(ext))) - 1, C64)
         both = torch.cat([sq, rt])
         comm.allreduce_sum(both)
-        sq, rt = both[:ktot], both[ktot:]
+        sq, rt = both[:kx], both[kx:]
         sq_h = sq.cpu().numpy()
         res = []
         for L in range(nL):
@@ -449,9 +480,14 @@ class GroupingEngine:
             lab = labels_all[L]
             comm.allgather_rows(lab, ctx.bounds)
             centers = (C_all[lo:hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()  # _kmeans.py:1543-1546
+            disp = None
+            if strict[L]:
+                disp = (sq[lo:hi], rt[lo:hi])
+            elif L in ext:
+                xlo = int(off_x[nL + ext.index(L)])
+                disp = (sq[xlo:xlo + ks[L]], rt[xlo:xlo + ks[L]])
             res.append(KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
-                                    n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L], csums=csums[L],
-                                    disp=(sq[lo:hi], rt[lo:hi]) if strict[L] else None))
+                                    n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L], csums=csums[L], disp=disp))
         return res
 
     # ------------------------------------------------------------------------------ a6, wide k-ranges on the tensor cores
@@ -817,6 +853,12 @@ class GroupingEngine:
         (perm int64 [P], chunk_cell int32 [P/32], cell_to_cluster int32 [nL, G], G, P)."""
         dev = self.device
         N = labels_list[0].numel()
+        tuples = 1
+        for k in ks:
+            tuples = min(tuples * int(k), 1 << 40)
+        if hasattr(self.K, 'build_cells') and tuples <= self.K.BUILD_CELLS_MAX_KEYS and len(ks) <= 32:
+            # narrow k-ranges (k = 2..6: 720 tuples): keys, histogram, layout and scatter in three launches, no sort
+            return self.K.build_cells(torch.stack([l.to(torch.int32) for l in labels_list]).contiguous(), [int(k) for k in ks])
         key = torch.zeros(N, dtype=torch.int64, device=dev)
         span = 1
         for lab, k in zip(labels_list, ks):
@@ -887,13 +929,16 @@ class GroupingEngine:
             K.shared_zero(base + 4 * ((n + 1) % 2), 4)
         return base + 4 * (n % 2)
 
-    def sil_scale(self, Xc):
+    def sil_scale(self, Xc, ctx=None):
         """Power-of-two scale s for the fp16 operand and the split of the half squared norms m = s^2 |x|^2 / 2
         that ride in the MMA as fp16 pieces m * 2^-shift against the constant 2^shift.
         Constraints: max |x| s <= 4096 (fp16 keeps 11 significant bits), pad_m = 4 max(m) * 2^-shift <= 32768
         with shift <= 15.  Returns (scale, shift, pad_m)."""
-        amax = float(self.K.absmax(Xc).item())
-        max_sqn = float(self.K.row_sqnorms(Xc).max().item())
+        if ctx is not None and getattr(ctx, 'amax', None) is not None and getattr(ctx, 'max_sqn', None) is not None:
+            amax, max_sqn = ctx.amax, ctx.max_sqn                          # from the centring pass: no kernel, no sync
+        else:
+            amax = float(self.K.absmax(Xc).item())
+            max_sqn = float(self.K.row_sqnorms(Xc).max().item())
         if amax <= 0.0 or max_sqn <= 0.0:
             return 1.0, 0, 1.0
         scale = 2.0 ** math.floor(math.log2(min(4096.0 / amax, math.sqrt(2.0 ** 28 / max_sqn))))
@@ -912,7 +957,7 @@ class GroupingEngine:
                     self._silhouette_tc(ctx, labels_list[h:], ks[h:], counts_list[h:]))
         with self.span('sil_pack'):
             Xc = self._pad16(ctx.Xc, 64)                                      # whole 64-column k-blocks
-            scale, shift, pad_m = self.sil_scale(Xc)
+            scale, shift, pad_m = self.sil_scale(Xc, ctx)
             Xh, aug = K.sil_pack(Xc, perm, P, scale, shift, pad_m)
             cellsum = K.zeros((G, P), torch.float32)
         bounds = self._bounds(P // 128, 2)       # even row-block ranges: CTA pairs share one 256-row MMA

@@ -63,6 +63,14 @@ class CudaKernels:
         nv.call('vtf_center_rows', ptr(X), c_i64(N), c_int(d), ptr(mean32), ptr(out), stream())
         return out
 
+    def center_rows_stats(self, X, mean32):
+        """(Xc, stats): stats = fp32 [max |xc|, max row |xc|^2], computed in the centring pass."""
+        N, d = self._chk(X)
+        out = torch.empty_like(X)
+        stats = self.empty((2,), torch.float32)
+        nv.call('vtf_center_rows_stats', ptr(X), c_i64(N), c_int(d), ptr(mean32), ptr(out), None, ptr(stats), stream())
+        return out, stats
+
     def gather_rows(self, X, idx):
         N, d = self._chk(X)
         out = self.empty((idx.numel(), d), torch.float32)
@@ -269,6 +277,29 @@ class CudaKernels:
         ws = self._workspace(64)
         nv.call('vtf_cell_sums', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
                 c_int(len(k_off) - 1), koff, active, two_s, ptr(acc), None, ptr(ws), stream())
+
+    BUILD_CELLS_MAX_KEYS = 4096
+
+    def build_cells(self, labels_all, ks):
+        """Cell layout of the silhouette sweep for labels_all int32 [n_lab, N] (prod(ks) <= 4096): returns
+        (perm int64 [P], chunk_cell int32 [P/32], cell_to_cluster int32 [n_lab, G], G, P).  One small D2H (G, P)."""
+        import numpy as np
+        nL, N = labels_all.shape
+        tuples = 1
+        for k in ks:
+            tuples *= int(k)
+        g_max = min(tuples, N)
+        cap = ((N + 31 * g_max + 255) // 256) * 256
+        perm = self.empty((cap,), torch.int64)
+        chunk_cell = self.empty((cap // 32,), torch.int32)
+        c2c = self.empty((nL, g_max), torch.int32)
+        meta = self.empty((3,), torch.int64)
+        ws = self._workspace(nv.load().vtf_build_cells_ws_bytes(N))
+        keep, kh = self._koff(np.asarray(ks, dtype=np.int32))
+        nv.call('vtf_build_cells', ptr(labels_all), c_i64(labels_all.stride(0)), c_i64(N), c_int(nL), kh, ptr(perm), c_i64(cap),
+                ptr(chunk_cell), ptr(c2c), c_int(g_max), ptr(meta), ptr(ws), stream())
+        G, P, _ = (int(v) for v in meta.cpu().tolist())
+        return perm[:P], chunk_cell[:P // 32], c2c[:, :G].contiguous(), G, P
 
     # ------------------------------------------------------------------ a3 / a1
     def cosine_classify(self, Xn, Rn, thr):
