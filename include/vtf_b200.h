@@ -65,7 +65,10 @@ int vtf_center_rows_stats(const float* X, int64_t N, int d, const float* mean, f
  * pots[t] = sum_i out[t,i] accumulated in fp64 (:263).  ws: vtf_kpp_ws_bytes(T).           */
 size_t vtf_kpp_ws_bytes(int T);
 int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T,
-                 const float* closest, float* out, double* pots, void* ws, void* stream);
+                 const float* closest, const double* xsq, float* out, double* pots, void* ws, void* stream);
+/* xsq[i] = |x_i|^2 in fp64, accumulated in the order vtf_kpp_dist uses: computed once per fit and passed to every
+ * round (nullable there: NULL recomputes it in the pass, same bits).                                          */
+int vtf_kpp_rownorm64(const float* Xc, int64_t N, int d, double* xsq, void* stream);
 /* kpp_pick: idx[t] = searchsorted(cumsum_fp32_sequential(closest), thr[t]) clipped to N-1
  * (:250-254).  thr must be ascending.  `offset_in`/`total_out` chain shards: the running
  * fp32 sum enters as *offset_in (NULL = 0) and leaves in *total_out (nullable); idx[t] = -1
@@ -324,6 +327,14 @@ int vtf_shared_open(const unsigned char handle[64], void** ptr);
 int vtf_shared_zero(void* ptr, size_t bytes, void* stream);
 int vtf_shared_close(void* ptr);
 int vtf_shared_free(void* ptr);
+
+/* ---- f4: output stage (grouping.py:78-84, 122-137; dupes.py:70-79) -- HOST code, no kernel -----------------------
+ * A batch of independent file operations on native threads: op 0 = copy src -> dst (shutil.copyfile: contents only,
+ * copy_file_range with a read/write fallback), 1 = move (os.replace), 2 = remove (os.remove; dst ignored).  Paths are
+ * NUL-terminated strings inside a host blob, path i at blob + off[i].  Every operation is attempted; returns the number
+ * of failures (-1: bad arguments) and reports the lowest failing index with its errno.                       */
+int64_t vtf_file_ops(int op, const char* src_blob_h, const int64_t* src_off_h, const char* dst_blob_h,
+                     const int64_t* dst_off_h, int64_t n, int threads, int64_t* first_index_h, int* first_errno_h);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,7 @@ class FakeKernels:
     def gather_rows(self, X, idx):
         return X[idx].contiguous()
 
-    def kpp_dist(self, Xc, cand, closest):
+    def kpp_dist(self, Xc, cand, closest, xsq=None):
         d = R.euclidean_sq_upcast(_np(cand), _np(Xc))
         if closest is not None:
             d = np.minimum(d, _np(closest)[None, :])

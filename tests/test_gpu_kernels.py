@@ -389,7 +389,7 @@ def test_center_rows_with_stats(K, N, d):
     (3000, 768, [2, 3, 4, 5, 6], 0b10110),          # frozen labellings keep their sums; 2 column slices, the second half empty
     (1025, 1024, [7, 9, 11, 13], 0b1111),           # 9009 tuples: split into groups
     (777, 64, [48], 0b1),                           # the largest k one labelling may have
-    (2048, 130, [3, 2], 0b11),                      # d not a multiple of 4 * 32
+    (2048, 132, [3, 2], 0b11),                      # d not a multiple of 128
     (40000, 512, [2, 3, 4, 5, 6, 7, 8, 9, 10], 0b111111111),   # more than 8 labellings
 ])
 def test_cell_sums_kernel(K, N, d, ks, active):

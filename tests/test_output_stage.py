@@ -1,6 +1,6 @@
-"""the threaded output stage leaves the same directory tree as the reference's
-per-file loops (grouping.py:78-84, 122-137; dupes.py:70-79), and embeddings that are still on the device go through
-the drop-in entry points without a host copy and give the same results as host arrays."""
+"""the native batched output stage (vtf_file_ops) leaves the same directory tree as
+the reference's per-file loops (grouping.py:78-84, 122-137; dupes.py:70-79), and embeddings that are still on the device
+go through the drop-in entry points without a host copy and give the same results as host arrays."""
 import os
 import os.path as osp
 
@@ -31,10 +31,10 @@ def _make(root, n):
     return paths
 
 
-@pytest.mark.parametrize('threads', ['1', '8'])
+@pytest.mark.parametrize('threads', ['0', '1', '8'])
 def test_copy_move_remove_match_the_plain_loops(tmp_path, monkeypatch, threads):
     monkeypatch.setenv('VTF_IO_THREADS', threads)
-    n = 1500                                   # > 2 chunks of 256, so the pool is used when threads > 1
+    n = 1500                                   # above VTF_IO_MIN_BATCH: the native batch runs unless threads == 0
     paths = _make(str(tmp_path / 'a'), n)
     labels = np.random.default_rng(0).integers(0, 5, n)
     for j in range(5):
@@ -72,8 +72,33 @@ def test_errors_surface_after_the_batch(tmp_path, monkeypatch):
 def test_io_threads_env(monkeypatch):
     monkeypatch.setenv('VTF_IO_THREADS', '3')
     assert fileops.io_threads() == 3
+    monkeypatch.setenv('VTF_IO_THREADS', '0')
+    assert fileops.io_threads() == 0                      # the reference's plain Python loop
     monkeypatch.delenv('VTF_IO_THREADS')
-    assert fileops.io_threads() == 1                      # default: the reference's plain loop (measured faster here)
+    assert 1 <= fileops.io_threads() <= 8                 # default: native batch (measured 2.8x / 5.4x faster, profiles/r02_fileops_bench.json)
+
+
+def test_native_batch_semantics(tmp_path, monkeypatch):
+    """copyfile semantics of the native path: contents only, existing destinations are overwritten, empty files and
+    non-ASCII names work, a failing move reports the first failing path."""
+    monkeypatch.setenv('VTF_IO_THREADS', '4')
+    monkeypatch.setattr(fileops, 'MIN_BATCH', 1)
+    src = tmp_path / 's'
+    dst = tmp_path / 'd'
+    src.mkdir(); dst.mkdir()
+    names = ['a.jpg', 'пример.png', 'empty.bin', 'big.bin']
+    (src / names[0]).write_bytes(b'x' * 10)
+    (src / names[1]).write_bytes(b'y' * 70000)
+    (src / names[2]).write_bytes(b'')
+    (src / names[3]).write_bytes(os.urandom(3 << 20))
+    (dst / names[0]).write_bytes(b'old content that is longer than the new one')
+    fileops.copy_files((str(src / n), str(dst / n)) for n in names)
+    for n in names:
+        assert (dst / n).read_bytes() == (src / n).read_bytes()
+    with pytest.raises(FileNotFoundError) as ei:
+        fileops.move_files([(str(src / 'a.jpg'), str(dst / 'moved.jpg')), (str(src / 'missing'), str(dst / 'x')), (str(src / 'big.bin'), str(dst / 'b2'))])
+    assert ei.value.filename == str(src / 'missing')
+    assert (dst / 'moved.jpg').exists() and (dst / 'b2').exists()      # the rest of the batch was still carried out
 
 
 @pytest.mark.gpu

@@ -79,6 +79,10 @@ def main():
     add('col_stats', lambda: K.col_stats(X), B)
     add('center_rows', lambda: K.center_rows(X, mean), 2 * B)
     add('kpp_dist T=3', lambda: K.kpp_dist(X, X[:3].contiguous(), closest), B + 3 * N * 4 + N * 4)
+    xsq = K.kpp_rownorm64(X)
+    add('kpp_rownorm64 (once per fit)', lambda: K.kpp_rownorm64(X), B + N * 8)
+    add('kpp_dist T=3 with precomputed |x|^2', lambda: K.kpp_dist(X, X[:3].contiguous(), closest, xsq), B + 3 * N * 4 + N * 12)
+    add('kpp_dist T=2 with precomputed |x|^2', lambda: K.kpp_dist(X, X[:2].contiguous(), closest, xsq), B + 2 * N * 4 + N * 12)
     add('kpp_pick (exact block scan)', lambda: K.kpp_pick(closest, thr), N * 4)
     add('kpp_pick_serial (one-thread chain)', lambda: K.kpp_pick(closest, thr, serial=True), N * 4)
     add('lloyd_assign k=%d' % k, lambda: K.lloyd_assign(X, C, labels, counts, nch), B + N * 8, 2.0 * N * k * d)

@@ -15,22 +15,41 @@ namespace vtf {
 
 constexpr int kMaxTrials = 8;
 
-template <int TT, int R>   // TT = compile-time bound on the number of candidates, R = rows per warp and pass
+// |x_row|^2 in fp64, in exactly the order kpp_dist_kernel accumulates it (lane-strided float4, four FMAs each, butterfly
+// warp_sum): computed once per fit context and handed to every seeding round instead of being recomputed 8 to 61 times.
+__global__ void __launch_bounds__(256) kpp_rownorm64_kernel(const float* __restrict__ X, int64_t N, int d, double* __restrict__ xsq) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = d >> 2;
+    int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (; row < N; row += stride) {
+        const float4* xr = reinterpret_cast<const float4*>(X + row * d);
+        double xx = 0.0;
+        for (int v = lane; v < nvec; v += 32) {
+            const float4 f = ldg_stream(xr + v);
+            const double a0 = f.x, a1 = f.y, a2 = f.z, a3 = f.w;
+            xx = fma(a0, a0, xx); xx = fma(a1, a1, xx); xx = fma(a2, a2, xx); xx = fma(a3, a3, xx);
+        }
+        xx = warp_sum(xx);
+        if (lane == 0) xsq[row] = xx;
+    }
+}
+
+template <int TT, int R, bool HAVE_XSQ>   // TT = compile-time bound on the number of candidates, R = rows per warp and pass
 __global__ void __launch_bounds__(256, 2) kpp_dist_kernel(const float* __restrict__ X, int64_t N, int d,
                                                        const float* __restrict__ cand, int T,
-                                                       const float* __restrict__ closest, float* __restrict__ out,
-                                                       double* __restrict__ part) {
-    extern __shared__ __align__(16) float sc[];   // [T][d] candidates
+                                                       const float* __restrict__ closest, const double* __restrict__ xsq,
+                                                       float* __restrict__ out, double* __restrict__ part) {
+    extern __shared__ __align__(16) double sc[];   // [T][d] candidates, converted to fp64 once per CTA
     __shared__ double s_cc[kMaxTrials];
     __shared__ double s_pot[8][kMaxTrials];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = d >> 2;
-    for (int i = threadIdx.x; i < T * nvec; i += blockDim.x)
-        reinterpret_cast<float4*>(sc)[i] = __ldg(reinterpret_cast<const float4*>(cand) + i);
+    for (int i = threadIdx.x; i < T * d; i += blockDim.x) sc[i] = (double)__ldg(cand + i);
     __syncthreads();
     if (warp < T) {
         double s = 0.0;
-        for (int j = lane; j < d; j += 32) { double c = (double)sc[warp * d + j]; s = fma(c, c, s); }
+        for (int j = lane; j < d; j += 32) { const double c = sc[warp * d + j]; s = fma(c, c, s); }
         s = warp_sum(s);
         if (lane == 0) s_cc[warp] = s;
     }
@@ -40,7 +59,7 @@ __global__ void __launch_bounds__(256, 2) kpp_dist_kernel(const float* __restric
 #pragma unroll
     for (int t = 0; t < TT; ++t) pot[t] = 0.0;
 
-    // R rows per warp and pass (4 for up to 4 candidates, 2 above: registers): every candidate float4 read from shared memory (and converted to fp64) serves R
+    // R rows per warp and pass (4 for up to 4 candidates, 2 above: registers): every candidate element read from shared memory serves R
     // rows -- the kernel was bound by those reads (T wavefronts per row and float4), not by HBM or the fp64 pipe.
     // Every row keeps its own accumulation order, so the results are bit-identical to the one-row form.
     int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * R;
@@ -62,18 +81,20 @@ __global__ void __launch_bounds__(256, 2) kpp_dist_kernel(const float* __restric
             for (int r = 0; r < R; ++r) {
                 const float4 f = ldg_stream(xr[r] + v);
                 a[r][0] = f.x; a[r][1] = f.y; a[r][2] = f.z; a[r][3] = f.w;
-                xx[r] = fma(a[r][0], a[r][0], xx[r]); xx[r] = fma(a[r][1], a[r][1], xx[r]);
-                xx[r] = fma(a[r][2], a[r][2], xx[r]); xx[r] = fma(a[r][3], a[r][3], xx[r]);
+                if (!HAVE_XSQ) {
+                    xx[r] = fma(a[r][0], a[r][0], xx[r]); xx[r] = fma(a[r][1], a[r][1], xx[r]);
+                    xx[r] = fma(a[r][2], a[r][2], xx[r]); xx[r] = fma(a[r][3], a[r][3], xx[r]);
+                }
             }
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
                 if (t < T) {
-                    const float4 c = reinterpret_cast<const float4*>(sc + (size_t)t * d)[v];
-                    const double cx = c.x, cy = c.y, cz = c.z, cw = c.w;
+                    const double2 c01 = reinterpret_cast<const double2*>(sc + (size_t)t * d)[2 * v];
+                    const double2 c23 = reinterpret_cast<const double2*>(sc + (size_t)t * d)[2 * v + 1];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        dot[r][t] = fma(a[r][0], cx, dot[r][t]); dot[r][t] = fma(a[r][1], cy, dot[r][t]);
-                        dot[r][t] = fma(a[r][2], cz, dot[r][t]); dot[r][t] = fma(a[r][3], cw, dot[r][t]);
+                        dot[r][t] = fma(a[r][0], c01.x, dot[r][t]); dot[r][t] = fma(a[r][1], c01.y, dot[r][t]);
+                        dot[r][t] = fma(a[r][2], c23.x, dot[r][t]); dot[r][t] = fma(a[r][3], c23.y, dot[r][t]);
                     }
                 }
             }
@@ -82,7 +103,7 @@ __global__ void __launch_bounds__(256, 2) kpp_dist_kernel(const float* __restric
         for (int r = 0; r < R; ++r) {
             const int64_t row = row0 + r;
             const bool have = row < N;                                    // warp-uniform
-            const double xs = warp_sum(xx[r]);
+            const double xs = HAVE_XSQ ? (have ? __ldg(xsq + row) : 0.0) : warp_sum(xx[r]);
             const float prev = (closest && have) ? __ldg(closest + row) : INFINITY;
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
@@ -400,20 +421,31 @@ extern "C" {
 
 size_t vtf_kpp_ws_bytes(int T) { return (size_t)kpp_grid() * (size_t)(T > 0 ? T : 1) * sizeof(double); }
 
-int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T, const float* closest, float* out,
+int vtf_kpp_rownorm64(const float* Xc, int64_t N, int d, double* xsq, void* stream) {
+    VTF_REQUIRE(Xc && xsq && N >= 0 && d > 0 && d % 4 == 0, "vtf_kpp_rownorm64");
+    if (N == 0) return VTF_OK;
+    const int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
+    VTF_LAUNCH(kpp_rownorm64_kernel, grid, 256, 0, stream, Xc, N, d, xsq);
+    VTF_CHECK_LAST("vtf_kpp_rownorm64");
+    return VTF_OK;
+}
+
+int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T, const float* closest, const double* xsq, float* out,
                  double* pots, void* ws, void* stream) {
     VTF_REQUIRE(Xc && cand && out && pots && ws && N >= 0 && d > 0 && d % 4 == 0 && T > 0 && T <= kMaxTrials,
                 "vtf_kpp_dist");
-    const size_t smem = (size_t)T * d * sizeof(float);
-    VTF_REQUIRE(smem <= 64 * 1024, "vtf_kpp_dist: T*d too large");
+    const size_t smem = (size_t)T * d * sizeof(double);
+    VTF_REQUIRE(smem <= 128 * 1024, "vtf_kpp_dist: T*d too large");
     const int grid = kpp_grid();
-    if (T <= 4) {
-        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "vtf_kpp_dist");
-        VTF_LAUNCH((kpp_dist_kernel<4, 4>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, out, (double*)ws);
-    } else {
-        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel<kMaxTrials, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "vtf_kpp_dist");
-        VTF_LAUNCH((kpp_dist_kernel<kMaxTrials, 2>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, out, (double*)ws);
-    }
+#define VTF_KPP_LAUNCH(TTv, Rv, Hv)                                                                                          \
+    do {                                                                                                                      \
+        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_kernel<TTv, Rv, Hv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024), \
+                 "vtf_kpp_dist");                                                                                             \
+        VTF_LAUNCH((kpp_dist_kernel<TTv, Rv, Hv>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, xsq, out, (double*)ws); \
+    } while (0)
+    if (T <= 4) { if (xsq) VTF_KPP_LAUNCH(4, 4, true); else VTF_KPP_LAUNCH(4, 4, false); }
+    else { if (xsq) VTF_KPP_LAUNCH(kMaxTrials, 2, true); else VTF_KPP_LAUNCH(kMaxTrials, 2, false); }
+#undef VTF_KPP_LAUNCH
     VTF_CHECK_LAST("vtf_kpp_dist");
     VTF_LAUNCH(reduce_parts_kernel, 1, 32, 0, stream, (const double*)ws, grid, T, pots, pots, T);
     VTF_CHECK_LAST("vtf_kpp_dist/reduce");

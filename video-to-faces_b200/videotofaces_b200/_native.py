@@ -25,7 +25,8 @@ SIGNATURES = {
     'vtf_build_cells_ws_bytes': (c_sz, [c_i64]),
     'vtf_build_cells': (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     'vtf_kpp_ws_bytes': (c_sz, [c_int]),
-    'vtf_kpp_dist': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_kpp_dist': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_kpp_rownorm64': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_kpp_pick': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vtf_contingency': (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'vtf_kpp_round_prep': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     'vtf_shared_close': (c_int, [c_vp]),
     'vtf_shared_free': (c_int, [c_vp]),
     'vtf_sil_finish_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'vtf_file_ops': (c_i64, [c_int, ctypes.c_char_p, c_vp, ctypes.c_char_p, c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_sil_finish_cells': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
 }
 

@@ -40,7 +40,7 @@ class KMeansResult:
 
 class FitContext:
     """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
-    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide', 'amax', 'max_sqn')
+    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide', 'amax', 'max_sqn', 'xsq')
 
 
 def n_local_trials(k):
@@ -309,7 +309,12 @@ class GroupingEngine:
         U = self.to_device(np.stack([rs.uniform(size=trials) for _ in range(1, k)]).reshape(max(k - 1, 0), trials),
                            torch.float64) if k > 1 else None
         closest = K.empty((N,), torch.float32)
-        out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None)     # _kmeans.py:240
+        xsq = None
+        if hasattr(K, 'kpp_rownorm64'):                                        # |x|^2 (fp64) of this rank's rows, once per fit
+            if getattr(ctx, 'xsq', None) is None:
+                ctx.xsq = K.kpp_rownorm64(ctx.Xc[b:e])
+            xsq = ctx.xsq
+        out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None, xsq)     # _kmeans.py:240
         chosen = []
         for r in range(k - 1):
             comm.allreduce_sum(pots)                                           # _kmeans.py:243 / :263
@@ -319,7 +324,7 @@ class GroupingEngine:
             if r > 0:
                 chosen.append(cand.index_select(0, best))                      # :270
             cand = K.kpp_unsort(K.kpp_pick(closest, thr), order, N)            # :250-254
-            out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand), closest[b:e])      # :257-263
+            out, pots = K.kpp_dist(ctx.Xc[b:e], K.gather_rows(ctx.Xc, cand), closest[b:e], xsq)      # :257-263
         seeds = [first]
         if k > 1:
             comm.allreduce_sum(pots)

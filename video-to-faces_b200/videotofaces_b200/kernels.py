@@ -78,13 +78,20 @@ class CudaKernels:
         return out
 
     # ------------------------------------------------------------------ a7
-    def kpp_dist(self, Xc, cand, closest):
+    def kpp_rownorm64(self, Xc):
+        """|x_row|^2 in fp64, in kpp_dist's own summation order (once per fit instead of once per seeding round)."""
+        N, d = self._chk(Xc)
+        out = self.empty((N,), torch.float64)
+        nv.call('vtf_kpp_rownorm64', ptr(Xc), c_i64(N), c_int(d), ptr(out), stream())
+        return out
+
+    def kpp_dist(self, Xc, cand, closest, xsq=None):
         N, d = self._chk(Xc)
         T = cand.shape[0]
         out = self.empty((T, N), torch.float32)
         pots = self.empty((T,), torch.float64)
         ws = self._workspace(nv.load().vtf_kpp_ws_bytes(T))
-        nv.call('vtf_kpp_dist', ptr(Xc), c_i64(N), c_int(d), ptr(cand), c_int(T), ptr(closest), ptr(out), ptr(pots),
+        nv.call('vtf_kpp_dist', ptr(Xc), c_i64(N), c_int(d), ptr(cand), c_int(T), ptr(closest), ptr(xsq), ptr(out), ptr(pots),
                 ptr(ws), stream())
         return out, pots
 
