@@ -75,6 +75,14 @@ int vtf_kpp_rownorm64(const float* Xc, int64_t N, int d, double* xsq, void* stre
  * when thr[t] is not reached inside this shard.                                            */
 int vtf_kpp_pick(const float* closest, int64_t N, const float* thr, int T,
                  const float* offset_in, float* total_out, int64_t* idx, void* stream);
+/* The same result again, with most of the array skipped: two multi-CTA passes compute, per tile of 8192 elements, the
+ * binade the running sum is expected to enter it with and the exact integer total of the rounded addends under that
+ * binade; the walk then jumps over every tile whose true incoming sum is in that binade, that does not carry it out of
+ * the binade and that holds no threshold, and scans only the rest (binade crossings, ties, threshold tiles: ~15 of 122 at
+ * 1M rows).  Bit-identical to vtf_kpp_pick / vtf_kpp_pick_serial.  ws: vtf_kpp_pick_ws_bytes(N).                  */
+size_t vtf_kpp_pick_ws_bytes(int64_t N);
+int vtf_kpp_pick_fast(const float* closest, int64_t N, const float* thr, int T, const float* offset_in,
+                      float* total_out, int64_t* idx, void* ws, void* stream);
 /* Round glue on the device (no host round trip per k-means++ round).  round_prep: best = argmin of the fp32-rounded
  * potentials of the previous round (:266, first minimum), pot = that potential; thr[t] = smallest fp32 >= u[t] * pot
  * (:249; u = the round's uniform draws, made in advance on the host by numpy's MT19937 -- they do not depend on the
@@ -196,6 +204,15 @@ int vtf_wide_update(const int64_t* acc, double inv_two_s, const int64_t* counts,
 int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
                   const int32_t* k_off_h, uint32_t active, double two_s, int64_t* acc, uint32_t* bad, void* ws,
                   void* stream);
+
+/* Dispersion for narrow k-ranges, organised by cells like vtf_cell_sums: out[slot] = sum_{i in slot} |x_i - C64[slot]|^2 *
+ * sq_unit and out[ktot + slot] = sum |x_i - C64[slot]| * rt_unit as int64 (fp64 arithmetic per row, then exact integer
+ * accumulation: the result does not depend on the order of rows, CTAs or ranks).  All n_lab labellings take part.  The
+ * units must keep the totals below 2^62 (sq_unit <= 2^62 / (rows in total * max |x - c|^2)).  d % 128 == 0, d <= 1024,
+ * k <= 48 per labelling.  ws: 64 + 2 * ktot * 8 bytes.  Replaces vtf_cluster_dispersion_multi on the default path.   */
+int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
+                        const int32_t* k_off_h, const double* C64, double sq_unit, double rt_unit, int64_t* out,
+                        uint32_t* bad, void* ws, void* stream);
 
 /* Cell layout of the silhouette sweep on the device (replaces a torch.unique / argsort chain): labels[n_lab][label_stride]
  * are ALL labellings of the k-range (k_h[q] clusters each, at most 4096 label tuples in total).  Occupied tuples = cells,

@@ -112,10 +112,39 @@ def test_kpp_pick_parallel_scan_is_bit_exact(K, name):
     thr = np.sort(thr)
     want = np.searchsorted(cs, thr, side='left').astype(np.int64)
     want[want >= v.size] = -1
-    for serial in (True, False):
-        idx, total = K.kpp_pick(dev(v), dev(thr), serial=serial, want_total=True)
-        assert np.array_equal(idx.cpu().numpy(), want), ('serial' if serial else 'scan', name)
-        assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), ('serial' if serial else 'scan', name)
+    for mode in ('serial', 'scan', 'fast'):                  # one-thread chain, block scan over every tile, tile skipping
+        idx, total = K.kpp_pick(dev(v), dev(thr), mode=mode, want_total=True)
+        assert np.array_equal(idx.cpu().numpy(), want), (mode, name)
+        assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), (mode, name)
+    # a shard of a longer chain: the running sum enters as an offset (and with it the binade the tiles were prepared for)
+    h = v.size // 2
+    cs2 = np.cumsum(np.concatenate([[cs[h - 1]], v[h:]]).astype(np.float32))[1:]
+    want2 = np.searchsorted(cs2, thr, side='left').astype(np.int64)
+    want2[thr <= cs[h - 1]] = -1                             # met by the earlier shard
+    want2[want2 >= v.size - h] = -1
+    for mode in ('scan', 'fast'):
+        idx, total = K.kpp_pick(dev(v[h:]), dev(thr), mode=mode, want_total=True, offset=dev(cs[h - 1:h]))
+        assert np.array_equal(idx.cpu().numpy(), want2), (mode, name, 'offset')
+        assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), (mode, name, 'offset')
+
+
+def test_kpp_pick_fast_on_many_seeds(K):
+    """Tile skipping against the sequential chain on k-means++-like distance vectors of 1-2 M elements, several seeds and
+    threshold sets (incl. thresholds just above / below tile boundaries of the running sum)."""
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        N = 1_000_000 + 8192 * seed + seed
+        v = (rng.standard_normal(N).astype(np.float32) ** 2 * np.float32(0.01 + 0.3 * seed) + np.float32(0.5)).astype(np.float32)
+        if seed % 2:
+            v[rng.random(N) < 0.3] = 0.0
+        cs = np.cumsum(v)
+        thr = np.sort(np.concatenate([(rng.random(3) * float(cs[-1])).astype(np.float32),
+                                      cs[[8191, 8192, 16 * 8192 - 1]], np.nextafter(cs[[40 * 8192]], np.float32(np.inf))]).astype(np.float32))
+        want = np.searchsorted(cs, thr, side='left').astype(np.int64)
+        want[want >= N] = -1
+        idx, total = K.kpp_pick(dev(v), dev(thr), mode='fast', want_total=True)
+        assert np.array_equal(idx.cpu().numpy(), want), seed
+        assert total.cpu().numpy()[0].tobytes() == cs[-1].tobytes(), seed
 
 
 @pytest.mark.parametrize('T', [1, 2, 3, 8])
@@ -450,3 +479,35 @@ def test_build_cells_kernel(engine, N, ks):
     lab_t = [dev(l) for l in labels]
     p2 = engine.build_cells(lab_t, ks)
     assert p2[3] == G and p2[4] == P
+
+
+@pytest.mark.parametrize('N,d,ks', [(5000, 512, [2, 3, 4, 5, 6]), (3001, 768, [2, 5]), (1500, 1024, [3, 4, 3]), (700, 128, [48]),
+                                    (20000, 512, [2, 3, 4, 5, 6, 2, 3])])
+def test_cell_dispersion_kernel(K, N, d, ks):
+    """Cell-wise dispersion (fp64 per row, exact fixed-point accumulation) against numpy fp64 and the warp-per-row kernel."""
+    rng = np.random.default_rng(N)
+    X = blobs(N, d, kc=5, seed=N, normalize=False)
+    base = rng.integers(0, 6, N)
+    labels = np.stack([(base + (rng.random(N) < 0.1)) % k for k in ks]).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(ks)]).astype(np.int32)
+    C64 = rng.standard_normal((int(off[-1]), d)) * 0.5
+    bound = 4.5 * float((X.astype(np.float64) ** 2).sum(1).max() + (C64 ** 2).sum(1).max())
+    sq_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (N * bound)))
+    rt_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (N * math.sqrt(bound))))
+    out = K.cell_dispersion(dev(X), dev(labels), 0, off, dev(C64), sq_unit, rt_unit).cpu().numpy()
+    ktot = int(off[-1])
+    sq, rt = out[:ktot] / sq_unit, out[ktot:] / rt_unit
+    wsq, wrt = np.zeros(ktot), np.zeros(ktot)
+    X64 = X.astype(np.float64)
+    for L, k in enumerate(ks):
+        d2 = ((X64 - C64[off[L] + labels[L]]) ** 2).sum(1)
+        np.add.at(wsq, off[L] + labels[L], d2)
+        np.add.at(wrt, off[L] + labels[L], np.sqrt(d2))
+    np.testing.assert_allclose(sq, wsq, rtol=1e-11)
+    np.testing.assert_allclose(rt, wrt, rtol=1e-11)
+    osq, ort = K.cluster_dispersion_multi(dev(X), dev(labels), 0, off, (1 << len(ks)) - 1, dev(C64))
+    np.testing.assert_allclose(sq, osq.cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(rt, ort.cpu().numpy(), rtol=1e-11)
+    # integers: a second run gives the same bits, whatever order the CTAs claimed their chunks in
+    out2 = K.cell_dispersion(dev(X), dev(labels), 0, off, dev(C64), sq_unit, rt_unit).cpu().numpy()
+    assert np.array_equal(out, out2)

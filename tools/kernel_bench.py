@@ -83,7 +83,8 @@ def main():
     add('kpp_rownorm64 (once per fit)', lambda: K.kpp_rownorm64(X), B + N * 8)
     add('kpp_dist T=3 with precomputed |x|^2', lambda: K.kpp_dist(X, X[:3].contiguous(), closest, xsq), B + 3 * N * 4 + N * 12)
     add('kpp_dist T=2 with precomputed |x|^2', lambda: K.kpp_dist(X, X[:2].contiguous(), closest, xsq), B + 2 * N * 4 + N * 12)
-    add('kpp_pick (exact block scan)', lambda: K.kpp_pick(closest, thr), N * 4)
+    add('kpp_pick (exact block scan)', lambda: K.kpp_pick(closest, thr, mode='scan'), N * 4)
+    add('kpp_pick fast (tile skipping)', lambda: K.kpp_pick(closest, thr, mode='fast'), 3 * N * 4)
     add('kpp_pick_serial (one-thread chain)', lambda: K.kpp_pick(closest, thr, serial=True), N * 4)
     add('lloyd_assign k=%d' % k, lambda: K.lloyd_assign(X, C, labels, counts, nch), B + N * 8, 2.0 * N * k * d)
     add('cluster_sums k=%d' % k, lambda: K.cluster_sums(X, labels, k), B + N * 4)
@@ -103,6 +104,10 @@ def main():
     labels_blob = torch.stack([(proj[:, :3] * torch.tensor([1, 2, 4], device='cuda', dtype=torch.int32)).sum(1) % kk for kk in ks]).to(torch.int32).contiguous()
     add('cell_sums k=2..6 (structured labels: <= 8 cells)', lambda: K.cell_sums(X, labels_blob, 0, off, 31, 2.0 ** 30, acc), B + 5 * N * 4)
     add('cell_sums k=6 alone', lambda: K.cell_sums(X, labels_all, 0, off, 16, 2.0 ** 30, acc), B + N * 4)
+    if d % 128 == 0 and d <= 1024:
+        C64a = C_all.double()
+        add('cell_dispersion k=2..6 (structured labels)', lambda: K.cell_dispersion(X, labels_blob, 0, off, C64a, 2.0 ** 30, 2.0 ** 30), B + 5 * N * 4)
+        add('cell_dispersion k=2..6 (random labels: 720 cells)', lambda: K.cell_dispersion(X, labels_all, 0, off, C64a, 2.0 ** 30, 2.0 ** 30), B + 5 * N * 4)
     add('cluster_dispersion_multi k=2..6', lambda: K.cluster_dispersion_multi(X, labels_all, 0, off, 31, C_all.double()), B + 5 * N * 4)
     # the same E-step as one tcgen05 contraction (csrc/lloyd_tc.cu): centre pack + split-fp16 assign + exact refine of near ties
     class _Ctx:

@@ -237,6 +237,225 @@ int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64
 
 }  // extern "C"
 
+namespace vtf {
+
+// ------------------------------------------------------------------------------------------------------------------
+// cell_dispersion_kernel: per cluster, sum of |x - c|^2 and of |x - c| over its rows (KMeans.inertia_, calinski_harabasz's
+// intra dispersion, davies_bouldin's distance sums; SK/cluster/_k_means_common.pyx:94-124, SK/metrics/cluster/
+// _unsupervised.py:394-399, 467-474) for several labellings in one pass.  Same chunking and grouping as cell_sums_kernel;
+// inside a cell every labelling measures against ONE centre, so a warp takes R rows of the cell at a time, keeps them in
+// registers and reads each centre element from shared memory (fp64, [slots][d]) once per R rows.  Differences, squares
+// and the lane-strided sum run in fp64, the per-row results are accumulated as 64-bit FIXED-POINT integers -- exact,
+// order-independent adds again, so the result does not depend on the scatter order, the CTA schedule or the rank count.
+// The kernel this replaces (cluster_dispersion_kernel, accumulate.cu) re-read fp64 centre rows through L1 for every row and
+// labelling: 0.16 of the HBM roofline for k = 2..6.
+template <int DV, int R>
+__global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const float* __restrict__ X, long long n, int d,
+                                                                          const int32_t* __restrict__ labels, const CellPlan pl,
+                                                                          const double* __restrict__ C64, double sq_unit, double rt_unit,
+                                                                          unsigned long long* __restrict__ out, unsigned int* __restrict__ bad,
+                                                                          unsigned int* __restrict__ claim) {
+    extern __shared__ __align__(16) unsigned char cell_smem[];
+    double* sc = reinterpret_cast<double*>(cell_smem);                                        // [n_slots][d] centres
+    long long* wacc = reinterpret_cast<long long*>(sc + (size_t)pl.n_slots * d);              // [8 warps][2][n_slots]
+    unsigned int* cursor = reinterpret_cast<unsigned int*>(wacc + 8 * 2 * pl.n_slots);
+    unsigned int* start = cursor + kCellKeys;
+    unsigned short* keys = reinterpret_cast<unsigned short*>(start + kCellKeys);
+    unsigned short* order = keys + kCellRows;
+    unsigned short* segkey = order + kCellRows;
+    __shared__ unsigned int warp_tot[kCellThreads / 32];
+    __shared__ int s_nseg;
+    __shared__ unsigned int s_chunk;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long n_chunks = (n + kCellRows - 1) / kCellRows;
+    for (int i = t; i < pl.n_slots * d; i += kCellThreads) sc[i] = C64[i];
+    for (int i = t; i < 8 * 2 * pl.n_slots; i += kCellThreads) wacc[i] = 0ll;
+    long long* my_sq = wacc + (size_t)warp * 2 * pl.n_slots;
+    long long* my_rt = my_sq + pl.n_slots;
+    unsigned int nbad = 0;
+    for (;;) {
+        if (t == 0) s_chunk = atomicAdd(claim, 1u);
+        for (int i = t; i < kCellKeys; i += kCellThreads) cursor[i] = 0u;
+        __syncthreads();
+        if ((long long)s_chunk >= n_chunks) break;
+        const long long row0 = (long long)s_chunk * kCellRows;
+        const int Rn = (int)min((long long)kCellRows, n - row0);
+        for (int i = t; i < Rn; i += kCellThreads) {
+            int key = 0;
+            for (int q = 0; q < pl.n_lab; ++q) {
+                int l = __ldg(labels + (long long)pl.row_of[q] * pl.label_stride + row0 + i);
+                if ((unsigned)l >= (unsigned)pl.kk[q]) { ++nbad; l = 0; }
+                key += l * pl.mult[q];
+            }
+            keys[i] = (unsigned short)key;
+            atomicAdd(&cursor[key], 1u);
+        }
+        __syncthreads();
+        unsigned int c4[4];
+        unsigned int local = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c4[j] = cursor[4 * t + j]; local += c4[j] + (c4[j] ? 0x10000u : 0u); }
+        unsigned int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned int base = incl - local;
+        for (int w = 0; w < warp; ++w) base += warp_tot[w];
+        if (t == kCellThreads - 1) s_nseg = (int)((base + local) >> 16);
+        {
+            unsigned int pos = base & 0xffffu, seg = base >> 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                start[4 * t + j] = pos;
+                cursor[4 * t + j] = pos;
+                if (c4[j]) segkey[seg++] = (unsigned short)(4 * t + j);
+                pos += c4[j];
+            }
+        }
+        __syncthreads();
+        for (int i = t; i < Rn; i += kCellThreads) order[atomicAdd(&cursor[keys[i]], 1u)] = (unsigned short)i;
+        __syncthreads();
+
+        const int nseg = s_nseg;
+        for (int s = 0; s < nseg; ++s) {
+            const int key = segkey[s];
+            const int st = (int)start[key], en = (int)cursor[key];
+            // the rows of the cell, R at a time per warp
+            for (int j = st + R * warp; j < en; j += R * (kCellThreads / 32)) {
+                float4 xv[R][DV];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int jj = min(j + r, en - 1);
+                    const float4* xr = reinterpret_cast<const float4*>(X + (size_t)(row0 + order[jj]) * d);
+#pragma unroll
+                    for (int v = 0; v < DV; ++v) xv[r][v] = __ldcs(xr + lane + 32 * v);
+                }
+                for (int q = 0; q < pl.n_lab; ++q) {
+                    const int slot = pl.slot0[q] + (key / pl.mult[q]) % pl.kk[q];
+                    const double2* cr = reinterpret_cast<const double2*>(sc + (size_t)slot * d);
+                    double acc[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+#pragma unroll
+                    for (int v = 0; v < DV; ++v) {
+                        const double2 c01 = cr[2 * (lane + 32 * v)], c23 = cr[2 * (lane + 32 * v) + 1];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            double e;
+                            e = (double)xv[r][v].x - c01.x; acc[r] = fma(e, e, acc[r]);
+                            e = (double)xv[r][v].y - c01.y; acc[r] = fma(e, e, acc[r]);
+                            e = (double)xv[r][v].z - c23.x; acc[r] = fma(e, e, acc[r]);
+                            e = (double)xv[r][v].w - c23.y; acc[r] = fma(e, e, acc[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+                    if (lane == 0) {
+                        long long a_sq = 0, a_rt = 0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (j + r < en) {
+                                a_sq += __double2ll_rn(acc[r] * sq_unit);
+                                a_rt += __double2ll_rn(sqrt(acc[r]) * rt_unit);
+                            }
+                        }
+                        my_sq[slot] += a_sq;
+                        my_rt[slot] += a_rt;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (nbad && bad) atomicAdd(bad, nbad);
+    __syncthreads();
+    for (int i = t; i < 2 * pl.n_slots; i += kCellThreads) {
+        long long v = 0;
+        for (int w = 0; w < 8; ++w) v += wacc[(size_t)w * 2 * pl.n_slots + i];
+        if (v) atomicAdd(out + i, (unsigned long long)v);
+    }
+}
+
+}  // namespace vtf
+
+extern "C" {
+
+// out[0 .. ktot) = sum |x - c|^2 * sq_unit, out[ktot .. 2 ktot) = sum |x - c| * rt_unit per cluster slot, as int64 (zeroed here).
+// All n_lab labellings take part (one group of at most 8 labellings / 1024 label tuples / 48 slots per launch; d % 128 == 0,
+// d <= 1024).  The units must keep every sum below 2^62: sq_unit <= 2^62 / (n_total * max d2), likewise rt_unit.
+int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
+                        const int32_t* k_off_h, const double* C64, double sq_unit, double rt_unit, int64_t* out, uint32_t* bad,
+                        void* ws, void* stream) {
+    VTF_REQUIRE(X && labels && k_off_h && C64 && out && ws && n >= 0 && d > 0 && d % 128 == 0 && d <= 1024 && n_lab > 0 &&
+                    n_lab <= kMaxSeg && label_stride >= n && k_off_h[0] == 0 && sq_unit > 0.0 && rt_unit > 0.0,
+                "vtf_cell_dispersion (d % 128 == 0, d <= 1024)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ktot = k_off_h[n_lab];
+    VTF_CUDA(cudaMemsetAsync(out, 0, (size_t)2 * ktot * sizeof(int64_t), st), "vtf_cell_dispersion/zero");
+    if (bad) VTF_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st), "vtf_cell_dispersion/zero");
+    if (n == 0) return VTF_OK;
+    int L = 0, launch = 0;
+    while (L < n_lab) {
+        CellPlan pl = {};
+        const int L0 = L;
+        long long keys = 1;
+        while (L < n_lab) {
+            const int k = k_off_h[L + 1] - k_off_h[L];
+            VTF_REQUIRE(k > 0 && k <= kCellMaxSlots, "vtf_cell_dispersion: 1 <= k <= 48 per labelling");
+            const size_t need = (size_t)(k_off_h[L + 1] - k_off_h[L0]) * d * sizeof(double);
+            if (pl.n_lab > 0 && (pl.n_lab >= kCellMaxLab || keys * k > kCellKeys || need > 160 * 1024)) break;
+            VTF_REQUIRE(need <= 200 * 1024, "vtf_cell_dispersion: k * d too large");
+            pl.row_of[pl.n_lab] = L;
+            pl.slot0[pl.n_lab] = k_off_h[L] - k_off_h[L0];
+            pl.kk[pl.n_lab] = k;
+            pl.mult[pl.n_lab] = (int)keys;
+            keys *= k;
+            ++pl.n_lab;
+            ++L;
+        }
+        pl.n_slots = k_off_h[L] - k_off_h[L0];
+        pl.label_stride = label_stride;
+        const size_t smem = (size_t)pl.n_slots * d * sizeof(double) + (size_t)8 * 2 * pl.n_slots * sizeof(long long) +
+                            2 * kCellKeys * sizeof(unsigned int) + 2 * kCellRows * sizeof(unsigned short) + kCellKeys * sizeof(unsigned short);
+        VTF_REQUIRE(launch < 16, "vtf_cell_dispersion: too many groups");
+        unsigned int* claim = reinterpret_cast<unsigned int*>(ws) + launch;
+        VTF_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), st), "vtf_cell_dispersion/claim");
+        const long long chunks = (n + kCellRows - 1) / kCellRows;
+        const unsigned grid = (unsigned)max(1ll, min(chunks, (long long)num_sms()));
+        // sq and rt of this group's slots live at out[k_off[L0] ..] and out[ktot + k_off[L0] ..]: the kernel writes [2][n_slots]
+        // contiguously, so groups other than the only one go through a scratch area in ws and are scattered by a copy
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(out);
+        const bool whole = (L0 == 0 && L == n_lab);
+        unsigned long long* tmp = whole ? dst : reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + 64) + (size_t)2 * k_off_h[L0];
+        if (!whole) VTF_CUDA(cudaMemsetAsync(tmp, 0, (size_t)2 * pl.n_slots * sizeof(int64_t), st), "vtf_cell_dispersion/tmp");
+#define VTF_CD_CASE(DVv, Rv)                                                                                                        \
+    case DVv:                                                                                                                       \
+        VTF_CUDA(cudaFuncSetAttribute(cell_dispersion_kernel<DVv, Rv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),     \
+                 "vtf_cell_dispersion/smem");                                                                                       \
+        VTF_LAUNCH((cell_dispersion_kernel<DVv, Rv>), grid, kCellThreads, smem, stream, X, (long long)n, d, labels, pl,             \
+                   C64 + (size_t)k_off_h[L0] * d, sq_unit, rt_unit, tmp, bad, claim);                                               \
+        break;
+        switch (d / 128) {
+            VTF_CD_CASE(1, 4) VTF_CD_CASE(2, 4) VTF_CD_CASE(3, 4) VTF_CD_CASE(4, 4)
+            VTF_CD_CASE(5, 2) VTF_CD_CASE(6, 2) VTF_CD_CASE(7, 2) VTF_CD_CASE(8, 2)
+        }
+#undef VTF_CD_CASE
+        VTF_CHECK_LAST("vtf_cell_dispersion");
+        if (!whole) {
+            VTF_CUDA(cudaMemcpyAsync(out + k_off_h[L0], tmp, (size_t)pl.n_slots * sizeof(int64_t), cudaMemcpyDeviceToDevice, st),
+                     "vtf_cell_dispersion/copy");
+            VTF_CUDA(cudaMemcpyAsync(out + ktot + k_off_h[L0], tmp + pl.n_slots, (size_t)pl.n_slots * sizeof(int64_t),
+                                     cudaMemcpyDeviceToDevice, st), "vtf_cell_dispersion/copy");
+        }
+        ++launch;
+    }
+    return VTF_OK;
+}
+
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------------------------------
 // Cell layout of the silhouette sweep (gram_tc.cu): rows grouped by their joint label tuple over ALL labellings of the
 // k-range, every cell padded to a multiple of 32 positions, the total to a multiple of 256.  Three launches, no sort:

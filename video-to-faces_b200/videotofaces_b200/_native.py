@@ -28,6 +28,8 @@ SIGNATURES = {
     'vtf_kpp_dist': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_kpp_rownorm64': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'vtf_kpp_pick': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_kpp_pick_ws_bytes': (c_sz, [c_i64]),
+    'vtf_kpp_pick_fast': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_contingency': (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'vtf_kpp_round_prep': (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vtf_kpp_unsort': (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
@@ -55,6 +57,8 @@ SIGNATURES = {
     'vtf_wide_update': (c_int, [c_vp, ctypes.c_double, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_int,
                                 c_vp]),
     'vtf_cell_sums': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, ctypes.c_double, c_vp, c_vp, c_vp, c_vp]),
+    'vtf_cell_dispersion': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
+                                    c_vp, c_vp]),
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),

@@ -474,10 +474,7 @@ class GroupingEngine:
             C64 = torch.cat([C64] + means).contiguous()
             off_x = np.concatenate([off, off[-1] + np.cumsum([ks[L] for L in ext])]).astype(np.int32)
         kx = int(off_x[-1])
-        sq, rt = K.cluster_dispersion_multi(Xs, labels_x, b, off_x, (1 << (nL + len(ext))) - 1, C64)
-        both = torch.cat([sq, rt])
-        comm.allreduce_sum(both)
-        sq, rt = both[:kx], both[kx:]
+        sq, rt = self._dispersion(ctx, Xs, labels_x, b, off_x, [ks[L] for L in range(nL)] + [ks[L] for L in ext], C64)
         sq_h = sq.cpu().numpy()
         res = []
         for L in range(nL):
@@ -691,6 +688,26 @@ class GroupingEngine:
                                       n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L],
                                       csums=csums[lo0 + lo:lo0 + hi], disp=(sq[lo:hi], rt[lo:hi]) if strict[L] else None)
         return res
+
+    def _dispersion(self, ctx, Xs, labels_x, b, off_x, ks_x, C64):
+        """(sq, rt) fp64 [sum k], all-reduced: per cluster the sums of |x - c|^2 and |x - c| over this fit context's rows.
+        Narrow k-ranges run cell-wise with exact fixed-point accumulation (csrc/cells.cu); the units follow from the largest
+        squared row norm of the centred matrix (centres are means of rows, so |x - c|^2 <= 4 max |x|^2)."""
+        K, comm = self.K, self.comm
+        kx = int(off_x[-1])
+        max_sqn = getattr(ctx, 'max_sqn', None)
+        if (max_sqn and max_sqn > 0.0 and hasattr(K, 'cell_dispersion') and K.cell_dispersion_ok(ctx.d, ks_x) and
+                labels_x.shape[0] <= 32):
+            bound = 4.5 * max_sqn
+            sq_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (max(ctx.N, 2) * bound)))
+            rt_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (max(ctx.N, 2) * math.sqrt(bound))))
+            out = K.cell_dispersion(Xs, labels_x, b, off_x, C64, sq_unit, rt_unit)
+            comm.allreduce_sum(out)                                            # integers: exact in any order
+            return out[:kx].to(torch.float64) / sq_unit, out[kx:].to(torch.float64) / rt_unit
+        sq, rt = K.cluster_dispersion_multi(Xs, labels_x, b, off_x, (1 << labels_x.shape[0]) - 1, C64)
+        both = torch.cat([sq, rt])
+        comm.allreduce_sum(both)
+        return both[:kx], both[kx:]
 
     def _relocate_empty(self, ctx, labels, C_old, sums, counts, n_changed, st):
         """SK/cluster/_k_means_common.pyx:167-211: give every empty cluster the point farthest from

@@ -95,12 +95,21 @@ class CudaKernels:
                 ptr(ws), stream())
         return out, pots
 
-    def kpp_pick(self, closest, thr32, serial=False, want_total=False):
+    def kpp_pick(self, closest, thr32, serial=False, want_total=False, mode=None, offset=None):
+        """mode: 'fast' (default: tile skipping), 'scan' (every tile through the block scan), 'serial' (one-thread chain);
+        all three give the same bits.  VTF_PICK_MODE overrides the default."""
+        import os
         T = thr32.numel()
         idx = self.empty((T,), torch.int64)
         total = self.empty((1,), torch.float32) if want_total else None
-        nv.call('vtf_kpp_pick_serial' if serial else 'vtf_kpp_pick', ptr(closest), c_i64(closest.numel()), ptr(thr32), c_int(T),
-                None, ptr(total), ptr(idx), stream())
+        mode = 'serial' if serial else (mode or os.environ.get('VTF_PICK_MODE', 'fast'))
+        if mode == 'fast':
+            ws = self._workspace(nv.load().vtf_kpp_pick_ws_bytes(closest.numel()))
+            nv.call('vtf_kpp_pick_fast', ptr(closest), c_i64(closest.numel()), ptr(thr32), c_int(T), ptr(offset), ptr(total), ptr(idx),
+                    ptr(ws), stream())
+        else:
+            nv.call('vtf_kpp_pick_serial' if mode == 'serial' else 'vtf_kpp_pick', ptr(closest), c_i64(closest.numel()), ptr(thr32),
+                    c_int(T), ptr(offset), ptr(total), ptr(idx), stream())
         return (idx, total) if want_total else idx
 
     def kpp_round_prep(self, pots, u):
@@ -284,6 +293,21 @@ class CudaKernels:
         ws = self._workspace(64)
         nv.call('vtf_cell_sums', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
                 c_int(len(k_off) - 1), koff, active, two_s, ptr(acc), None, ptr(ws), stream())
+
+    def cell_dispersion_ok(self, d, ks):
+        return d % 128 == 0 and d <= 1024 and max(ks) <= self.CELL_MAX_K
+
+    def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit):
+        """int64 [2 * ktot]: per cluster slot sum |x - c|^2 * sq_unit, then sum |x - c| * rt_unit (exact integer sums of
+        per-row fp64 values: add across ranks as integers, then divide by the units)."""
+        n, d = self._chk(Xs)
+        keep, koff = self._koff(k_off)
+        ktot = int(k_off[-1])
+        out = self.empty((2 * ktot,), torch.int64)
+        ws = self._workspace(64 + 16 * ktot)
+        nv.call('vtf_cell_dispersion', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
+                c_int(len(k_off) - 1), koff, ptr(C64_all), sq_unit, rt_unit, ptr(out), None, ptr(ws), stream())
+        return out
 
     BUILD_CELLS_MAX_KEYS = 4096
 
