@@ -551,17 +551,21 @@ def run_config(cfg, args, env, steps, warmup, headline):
         alone = kind == 'dedup_classify'
         peak = pk['tf_burst'] if alone else pk['tf_sust']
         traffic, tsrc = committed_traffic(cfg, int(N), int(d), world)
-        executed = fl if dom == 'sil_sweep' else 3.0 * fl        # dedup: hi*hi + hi*lo + lo*hi per K step
+        dstats = getattr(eng.K, 'dedup_stats', None) or {}
+        # dedup: the single-MMA screen executes the algorithmic N^2*d once (plus three times the re-swept units' share);
+        # the split-fp16 sweep issues hi*hi + hi*lo + lo*hi per K step
+        executed = fl if dom == 'sil_sweep' else fl * (3.0 if dstats.get('mode') == 'split' else
+                                                       1.0 + 3.0 * dstats.get('reswept_units', 0) / max(dstats.get('units', 1), 1))
         rec['roofline'] = dict(
             bound='tensor', kernel=('sil_sweep_kernel' if dom == 'sil_sweep' else 'dedup_sweep_kernel') +
-            ' (tcgen05 cta_group::2 kind::f16, fp32 accumulate in TMEM)',
+            ' (tcgen05 cta_group::2 kind::f16, fp32 accumulate in TMEM)' + ('' if dom == 'sil_sweep' else ' [%s]' % dstats),
             achieved=executed / (t_ms * 1e-3) / 1e12, peak=peak, unit='TFLOP/s', frac=executed / (t_ms * 1e-3) / 1e12 / peak,
             achieved_algorithmic=alg / (t_ms * 1e-3) / 1e12, frac_algorithmic=alg / (t_ms * 1e-3) / 1e12 / peak,
             traffic=traffic, traffic_source=tsrc, ms_per_launch=t_ms, flop_per_launch_executed=executed, flop_per_launch_algorithmic=alg,
             share_of_step=t_ms * len(spans) / steps / ms_step,
             note=('achieved/frac count the MMA flops the kernel EXECUTES per rank; *_algorithmic count SURVEY 8(d)\'s figure (%s) per rank '
                   'in the same time. The symmetric sweep computes only the tiles on or above the diagonal, so its algorithmic fraction can '
-                  'exceed 1 -- skipped work, not speed; the dedup sweep issues three MMAs per K step (split fp16), so it executes 3x.'
+                  'exceed 1 -- skipped work, not speed; the dedup screen issues one MMA per K step (the split-fp16 sweep three).'
                   % ('2*N^2*d' if dom == 'sil_sweep' else 'N^2*d')),
             peak_source=pk['source'] + (' bf16_tflops (burst: kernel timed alone)' if alone else ' bf16_tflops_sustained (kernel timed inside a long step)'))
     rec['phase_roofline'] = phase_table(cfg, int(N), int(d), phases, pk, world, info)

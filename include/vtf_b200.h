@@ -253,6 +253,19 @@ int vtf_cosine_dedup_tc(const void* Hi, const void* Lo, int64_t N, int64_t P, in
 /* The tensor core accumulates fp32 with truncation (~3e-6 relative after 96 steps): refine re-evaluates
  * every owned row's winner, key[i] = (bits(clip(1 - xn_i.xn_j, 0, 2)) << 32) | j with an exact fp32 dot.  */
 int vtf_dedup_refine(const float* Xn, int64_t N, int d, int rank, int world, uint64_t* key, void* stream);
+/* Two-stage form (the default for large N): a SCREEN with one MMA per K step on the rounded operand Hi alone -- a third of
+ * the tensor work of vtf_cosine_dedup_tc -- that keeps, per owned row and column half, the four largest Gram values among the
+ * earlier rows: cand[N][8] = {float bits of g, column} (half 0 in descending order, then half 1; column 0xffffffff =
+ * none).  refine4 evaluates those candidates with exact fp32 dot products, writes key[i] = (bits(min dist) << 32) | first
+ * argmin, and flags unit_flag[i / 256] (*n_flagged += newly flagged units) for rows whose decision at `thr` the screen
+ * cannot guarantee: exact minimum above thr although an unseen column might be below (1 - g_unseen/scale^2 - eps <= thr;
+ * eps = bound of the screen's error, 1e-3 for unit rows; thr = NaN: never).  The flagged units are re-swept with the split
+ * operands by vtf_cosine_dedup_tc_units (unit_list: device array of unit indices) followed by vtf_dedup_refine.     */
+int vtf_dedup_screen(const void* Hi, int64_t N, int64_t P, int d, int rank, int world, void* cand, void* stream);
+int vtf_dedup_refine4(const float* Xn, int64_t N, int d, int rank, int world, const void* cand, float scale, float thr,
+                      float eps, uint64_t* key, int32_t* unit_flag, uint32_t* n_flagged, void* stream);
+int vtf_cosine_dedup_tc_units(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale,
+                              const int32_t* unit_list, int64_t n_list, uint64_t* key, void* stream);
 /* 'hash' branch (dupes.py:55-58; detection.py:57-59): bits[N,64] int64 0/1 average hashes (dupes.py:11-15)
  * -> packed[N] uint64; key[i] = (min_{j<i} popc(h_i ^ h_j) << 32) | argmin_j, row 0 = 10000 << 32 (the
  * reference's uint16 distance + 10000 mask).  Rows are owned in 256-row tiles, tile t by rank t % world.  */

@@ -511,3 +511,59 @@ def test_cell_dispersion_kernel(K, N, d, ks):
     # integers: a second run gives the same bits, whatever order the CTAs claimed their chunks in
     out2 = K.cell_dispersion(dev(X), dev(labels), 0, off, dev(C64), sq_unit, rt_unit).cpu().numpy()
     assert np.array_equal(out, out2)
+
+
+@pytest.mark.parametrize('N,d', [(9000, 512), (3000, 768), (700, 64)])
+def test_dedup_screen_equals_split_sweep(engine, N, d):
+    """Two-stage dedup (single-MMA screen + exact re-evaluation of the kept candidates) against the split-fp16 sweep and the
+    scikit-learn oracle: same duplicate set, same logged distances."""
+    K = engine.K
+    X = plant_dupes(blobs(N, d, kc=4, seed=5, normalize=(d == 512)), frac=20, seed=1, normalize=(d == 512))[0]
+    Xn = K.normalize_rows(dev(X))
+    thr = np.float32(0.2)
+
+    def decode(key):
+        k = key.cpu().numpy()
+        return (k >> 32).astype(np.uint32).view(np.float32), (k & 0xffffffff).astype(np.int64)
+    m_scr, i_scr = decode(K.cosine_dedup_tc(Xn, 0, 1, float(thr), mode='screen'))
+    assert K.dedup_stats['mode'] == 'screen'
+    m_spl, i_spl = decode(K.cosine_dedup_tc(Xn, 0, 1, mode='split'))
+    rmins, rinds, ridx = RC.dedup_core(X, thr)
+    ties = np.abs(rmins - thr) <= 1e-6
+    for m in (m_scr, m_spl):
+        got = np.nonzero(m <= thr)[0]
+        assert np.array_equal(np.setdiff1d(got, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
+    np.testing.assert_allclose(m_scr, rmins, rtol=2e-6, atol=4e-7)
+    assert (i_scr == rinds).mean() > 0.99 and (i_scr == i_spl).mean() > 0.99
+
+
+def test_dedup_screen_flags_rows_it_cannot_decide(engine):
+    """Rows with two earlier neighbours inside the screen's error band right above the threshold cannot be decided by the
+    single-MMA pass: their units are re-swept with the split operands.  Built so that the band is hit on purpose: the
+    decisions must equal the oracle's either way, and the re-sweep must have happened."""
+    K = engine.K
+    rng = np.random.default_rng(3)
+    N, d, thr = 4096, 512, np.float32(0.2)
+    X = blobs(N, d, kc=4, seed=8)
+    for r in range(40):                                       # row i = 2000 + 50 r: two earlier rows at cos-dist thr + {2e-4, 6e-4}
+        i = 2000 + 50 * r
+        for j, delta in ((10 + 3 * r, 2e-4), (500 + 7 * r, 6e-4)):
+            c = 1.0 - (float(thr) + delta)
+            g = rng.standard_normal(d).astype(np.float64)
+            g -= g.dot(X[j].astype(np.float64)) * X[j].astype(np.float64)
+            g /= np.linalg.norm(g)
+            if j == 10 + 3 * r:
+                base = c * X[j].astype(np.float64) + np.sqrt(1 - c * c) * g
+                X[i] = base.astype(np.float32)
+            else:                                             # rotate row j towards row i instead, so that i keeps its first neighbour
+                xi = X[i].astype(np.float64)
+                g2 = rng.standard_normal(d)
+                g2 -= g2.dot(xi) * xi
+                g2 /= np.linalg.norm(g2)
+                X[j] = (c * xi + np.sqrt(1 - c * c) * g2).astype(np.float32)
+    mins, inds, idx = engine.dedup(X, float(thr), force='tc')
+    assert K.dedup_stats['mode'] == 'screen' and K.dedup_stats['reswept_units'] > 0
+    rmins, rinds, ridx = RC.dedup_core(X, thr)
+    ties = np.abs(rmins - thr) <= 1e-6
+    assert np.array_equal(np.setdiff1d(idx, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
+    np.testing.assert_allclose(mins, rmins, rtol=1e-4, atol=4e-7)

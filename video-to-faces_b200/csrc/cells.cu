@@ -322,6 +322,9 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
         for (int s = 0; s < nseg; ++s) {
             const int key = segkey[s];
             const int st = (int)start[key], en = (int)cursor[key];
+            int slot[kCellMaxLab];                               // the cluster slot of this cell in every labelling
+#pragma unroll
+            for (int q = 0; q < kCellMaxLab; ++q) slot[q] = q < pl.n_lab ? pl.slot0[q] + (key / pl.mult[q]) % pl.kk[q] : 0;
             // the rows of the cell, R at a time per warp
             for (int j = st + R * warp; j < en; j += R * (kCellThreads / 32)) {
                 float4 xv[R][DV];
@@ -332,38 +335,50 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
 #pragma unroll
                     for (int v = 0; v < DV; ++v) xv[r][v] = __ldcs(xr + lane + 32 * v);
                 }
-                for (int q = 0; q < pl.n_lab; ++q) {
-                    const int slot = pl.slot0[q] + (key / pl.mult[q]) % pl.kk[q];
-                    const double2* cr = reinterpret_cast<const double2*>(sc + (size_t)slot * d);
-                    double acc[R];
+                double acc[kCellMaxLab][R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+                for (int q = 0; q < kCellMaxLab; ++q)
 #pragma unroll
-                    for (int v = 0; v < DV; ++v) {
-                        const double2 c01 = cr[2 * (lane + 32 * v)], c23 = cr[2 * (lane + 32 * v) + 1];
+                    for (int r = 0; r < R; ++r) acc[q][r] = 0.0;
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            double e;
-                            e = (double)xv[r][v].x - c01.x; acc[r] = fma(e, e, acc[r]);
-                            e = (double)xv[r][v].y - c01.y; acc[r] = fma(e, e, acc[r]);
-                            e = (double)xv[r][v].z - c23.x; acc[r] = fma(e, e, acc[r]);
-                            e = (double)xv[r][v].w - c23.y; acc[r] = fma(e, e, acc[r]);
-                        }
-                    }
+                for (int v = 0; v < DV; ++v) {
+                    double x64[R][4];                            // converted once, used by every labelling
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-                    if (lane == 0) {
-                        long long a_sq = 0, a_rt = 0;
+                    for (int r = 0; r < R; ++r) { x64[r][0] = xv[r][v].x; x64[r][1] = xv[r][v].y; x64[r][2] = xv[r][v].z; x64[r][3] = xv[r][v].w; }
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (j + r < en) {
-                                a_sq += __double2ll_rn(acc[r] * sq_unit);
-                                a_rt += __double2ll_rn(sqrt(acc[r]) * rt_unit);
+                    for (int q = 0; q < kCellMaxLab; ++q) {
+                        if (q < pl.n_lab) {                      // uniform branch
+                            const double2* cr = reinterpret_cast<const double2*>(sc + (size_t)slot[q] * d) + 2 * (lane + 32 * v);
+                            const double2 c01 = cr[0], c23 = cr[1];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                double e;
+                                e = x64[r][0] - c01.x; acc[q][r] = fma(e, e, acc[q][r]);
+                                e = x64[r][1] - c01.y; acc[q][r] = fma(e, e, acc[q][r]);
+                                e = x64[r][2] - c23.x; acc[q][r] = fma(e, e, acc[q][r]);
+                                e = x64[r][3] - c23.y; acc[q][r] = fma(e, e, acc[q][r]);
                             }
                         }
-                        my_sq[slot] += a_sq;
-                        my_rt[slot] += a_rt;
                     }
+                }
+                // lane q * R + r takes the (labelling q, row r) result: square root and fixed-point conversion run on up to 32
+                // lanes at once instead of one after the other on lane 0
+                double mine = 0.0;
+                int my_slot = 0;
+                bool have = false;
+#pragma unroll
+                for (int q = 0; q < kCellMaxLab; ++q) {
+                    if (q < pl.n_lab) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const double sum = warp_sum(acc[q][r]);
+                            if (lane == q * R + r) { mine = sum; my_slot = slot[q]; have = (j + r < en); }
+                        }
+                    }
+                }
+                if (have) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(my_sq + my_slot), (unsigned long long)__double2ll_rn(mine * sq_unit));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(my_rt + my_slot), (unsigned long long)__double2ll_rn(sqrt(mine) * rt_unit));
                 }
             }
         }

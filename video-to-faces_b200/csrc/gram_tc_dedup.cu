@@ -30,6 +30,8 @@ struct DedupParams {
     int64_t unit_stride;
     int n_kb;                  // d / 64
     float inv_s2;              // 1 / scale^2
+    const int32_t* unit_list;  // nullable: sweep exactly these units (the ones the single-MMA screen of gram_tc_screen.cu flagged)
+    int64_t n_list;
 };
 
 constexpr int kDStages = 3;
@@ -69,9 +71,11 @@ dedup_sweep_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     // this pair's units: positions pos = pair_id, pair_id + n_pairs, ... in this rank's list; unit = descending order
-    const int64_t n_mine = (prm.n_units - prm.unit_begin + prm.unit_stride - 1) / prm.unit_stride;
+    const int64_t n_mine = prm.unit_list ? prm.n_list : (prm.n_units - prm.unit_begin + prm.unit_stride - 1) / prm.unit_stride;
     const int64_t pair0 = blockIdx.x / 2, n_pairs = gridDim.x / 2;
-    auto unit_of = [&](int64_t pos) { return prm.n_units - 1 - (prm.unit_begin + pos * prm.unit_stride); };
+    auto unit_of = [&](int64_t pos) {
+        return prm.unit_list ? (int64_t)prm.unit_list[pos] : prm.n_units - 1 - (prm.unit_begin + pos * prm.unit_stride);
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -272,11 +276,28 @@ int vtf_dedup_pack(const float* Xn, int64_t N, int d, int64_t P, float scale, vo
     return VTF_OK;
 }
 
+static int dedup_tc_launch(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale, int rank, int world,
+                           const int32_t* unit_list, int64_t n_list, uint64_t* key, void* stream);
+
 int vtf_cosine_dedup_tc(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale, int rank, int world,
                         uint64_t* key, void* stream) {
     VTF_REQUIRE(Hi && Lo && key && N >= 0 && P >= N && P % 256 == 0 && d >= 64 && d <= 4096 && d % 64 == 0 && scale > 0.f &&
                     world > 0 && rank >= 0 && rank < world,
                 "vtf_cosine_dedup_tc (P % 256 == 0, d % 64 == 0)");
+    return dedup_tc_launch(Hi, Lo, N, P, d, scale, rank, world, nullptr, 0, key, stream);
+}
+
+int vtf_cosine_dedup_tc_units(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale, const int32_t* unit_list,
+                              int64_t n_list, uint64_t* key, void* stream) {
+    VTF_REQUIRE(Hi && Lo && key && unit_list && n_list >= 0 && N >= 0 && P >= N && P % 256 == 0 && d >= 64 && d <= 4096 &&
+                    d % 64 == 0 && scale > 0.f,
+                "vtf_cosine_dedup_tc_units (P % 256 == 0, d % 64 == 0)");
+    if (n_list == 0) return VTF_OK;
+    return dedup_tc_launch(Hi, Lo, N, P, d, scale, 0, 1, unit_list, n_list, key, stream);
+}
+
+static int dedup_tc_launch(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale, int rank, int world,
+                           const int32_t* unit_list, int64_t n_list, uint64_t* key, void* stream) {
     if (N <= 1) return VTF_OK;
     int rc = vtf_device_check();
     if (rc != VTF_OK) return rc;
@@ -291,8 +312,10 @@ int vtf_cosine_dedup_tc(const void* Hi, const void* Lo, int64_t N, int64_t P, in
     prm.unit_stride = world;
     prm.n_kb = d / tc::BK;
     prm.inv_s2 = 1.f / (scale * scale);
-    if (prm.unit_begin >= prm.n_units) return VTF_OK;
-    const int64_t n_mine = (prm.n_units - prm.unit_begin + prm.unit_stride - 1) / prm.unit_stride;
+    prm.unit_list = unit_list;
+    prm.n_list = n_list;
+    if (!unit_list && prm.unit_begin >= prm.n_units) return VTF_OK;
+    const int64_t n_mine = unit_list ? n_list : (prm.n_units - prm.unit_begin + prm.unit_stride - 1) / prm.unit_stride;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), n_mine);
     const size_t smem = 1024 + (size_t)tc::kDStages * tc::kDStageBytes + 256;
     VTF_CUDA(cudaFuncSetAttribute(tc::dedup_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

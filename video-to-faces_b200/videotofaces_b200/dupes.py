@@ -35,7 +35,7 @@ def dedup_rows(X, threshold):
     if on_device:
         kept = eng.delete_rows(X, idx) if idx.size else X.clone()              # stays in HBM for the grouping that follows
     else:
-        kept = eng.delete_rows(X, idx).cpu().numpy() if idx.size else np.array(X, dtype=np.float32, copy=True)
+        kept = eng.to_host([eng.delete_rows(X, idx)])[0] if idx.size else np.array(X, dtype=np.float32, copy=True)
     return dict(kept=kept, idx=idx, mins=mins, inds=inds)
 
 

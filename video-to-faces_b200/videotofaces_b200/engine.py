@@ -40,7 +40,7 @@ class KMeansResult:
 
 class FitContext:
     """What KMeans.fit derives from X before seeding (SK/cluster/_kmeans.py:1473-1496), shared by every k."""
-    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide', 'amax', 'max_sqn', 'xsq')
+    __slots__ = ('X', 'Xc', 'N', 'd', 'd_orig', 'bounds', 'b', 'e', 'col_sum', 'mean64', 'mean32', 'tol', 'wide', 'amax', 'max_sqn', 'xsq', 'kpp_first')
 
 
 def n_local_trials(k):
@@ -132,6 +132,26 @@ class GroupingEngine:
                                            torch.int64: np.int64}[dtype])
         return torch.from_numpy(A).to(self.device, non_blocking=False)
 
+    def to_host(self, tensors):
+        """Device tensors -> numpy arrays with ONE synchronisation: every tensor is copied asynchronously into a persistent
+        pinned staging buffer (grown on demand, page-locked once -- a fresh pinned allocation per call costs more than the
+        copy it speeds up), the stream is waited for once, and the results are copied out into ordinary numpy arrays the
+        caller owns.  `.cpu()` per tensor stages through pageable memory and synchronises every time."""
+        if self.device.type != 'cuda':
+            return [t.detach().cpu().numpy() for t in tensors]
+        sizes = [((t.numel() * t.element_size() + 255) // 256) * 256 for t in tensors]
+        total = sum(sizes)
+        if getattr(self, '_stage', None) is None or self._stage.numel() < total:
+            self._stage = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        views, at = [], 0
+        for t, sz in zip(tensors, sizes):
+            v = self._stage[at:at + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t.contiguous(), non_blocking=True)
+            views.append(v)
+            at += sz
+        torch.cuda.current_stream().synchronize()
+        return [v.numpy().copy() for v in views]
+
     def upload_replicated(self, A):
         """Host matrix -> the same full matrix on every rank.  With several ranks each one uploads only its row
         shard over its own PCIe link and the shards are all-gathered over NVLink (2 GB: ~3 ms at 8 GPUs) instead
@@ -184,9 +204,12 @@ class GroupingEngine:
         with self.span('normalize'):
             Xn = self.K.normalize_rows(X)
         with self.span('dedup', flops=float(N) * N * d):
-            key = (self.K.cosine_dedup_tc if use_tc else self.K.cosine_dedup)(Xn, self.comm.rank, self.comm.world)
+            if use_tc:
+                key = self.K.cosine_dedup_tc(Xn, self.comm.rank, self.comm.world, float(np.float32(threshold)))
+            else:
+                key = self.K.cosine_dedup(Xn, self.comm.rank, self.comm.world)
         self.comm.allreduce_min(key)
-        key_h = key.cpu().numpy()
+        key_h = self.to_host([key])[0]
         mins = (key_h >> 32).astype(np.uint32).view(np.float32)
         inds = (key_h & 0xffffffff).astype(np.int64)
         idx = (mins <= np.float32(threshold)).nonzero()[0]                    # dupes.py:65, fp32 compare
@@ -253,7 +276,8 @@ class GroupingEngine:
             self.comm.allgather_rows(label, bounds)
         else:
             dist, label = d_loc, l_loc
-        return dist.cpu().numpy(), label.cpu().numpy()
+        dist_h, label_h = self.to_host([dist, label])
+        return dist_h, label_h
 
     def _my_rows(self, n, align=1):
         bounds = self._bounds(n, align)
@@ -314,7 +338,14 @@ class GroupingEngine:
             if getattr(ctx, 'xsq', None) is None:
                 ctx.xsq = K.kpp_rownorm64(ctx.Xc[b:e])
             xsq = ctx.xsq
-        out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None, xsq)     # _kmeans.py:240
+        # distances to the first centre (_kmeans.py:240): every fit of the sweep starts a fresh RandomState(rstate), so all
+        # seedings of a k-range pick the SAME first row -- one pass serves them all
+        cache = getattr(ctx, 'kpp_first', None)
+        if cache is not None and cache[0] == first:
+            out, pots = cache[1].clone(), cache[2].clone()
+        else:
+            out, pots = K.kpp_dist(ctx.Xc[b:e], ctx.Xc[first:first + 1], None, xsq)
+            ctx.kpp_first = (first, out.clone(), pots.clone())
         chosen = []
         for r in range(k - 1):
             comm.allreduce_sum(pots)                                           # _kmeans.py:243 / :263
@@ -673,20 +704,33 @@ class GroupingEngine:
         for grp in sum_groups:                                                 # _k_means_common.pyx:94-124
             g0, g1 = grp[0], grp[-1] + 1
             lo0, hi0 = int(off[g0]), int(off[g1])
-            sub_off = (off[g0:g1 + 1] - off[g0]).astype(np.int32)
-            sq, rt = K.cluster_dispersion_multi(Xs, labels_all[g0:g1], b, sub_off, (1 << (g1 - g0)) - 1, C64_all[lo0:hi0].contiguous())
-            both = torch.cat([sq, rt])
-            comm.allreduce_sum(both)
-            sq, rt = both[:hi0 - lo0], both[hi0 - lo0:]
+            # every labelling against its centres (inertia; for 'labels unchanged' fits also CH's intra dispersion and DB's
+            # distance sums); tolerance-stopped fits a second time against the fp64 means of their final labels
+            ext = [L for L in grp if not strict[L]][:32 - len(grp)]
+            labels_x = labels_all[g0:g1]
+            C64 = C64_all[lo0:hi0]
+            off_x = (off[g0:g1 + 1] - off[g0]).astype(np.int32)
+            if ext:
+                labels_x = torch.cat([labels_x, labels_all[ext]]).contiguous()
+                means = [csums[int(off[L]):int(off[L + 1])] / counts_fin[L].to(torch.float64).clamp_min(1).unsqueeze(1) for L in ext]
+                C64 = torch.cat([C64] + means).contiguous()
+                off_x = np.concatenate([off_x, off_x[-1] + np.cumsum([ks[L] for L in ext])]).astype(np.int32)
+            sq, rt = self._dispersion(ctx, Xs, labels_x, b, off_x, [ks[L] for L in grp] + [ks[L] for L in ext], C64.contiguous())
             sq_h = sq.cpu().numpy()
             for L in grp:
                 lo, hi = int(off[L]) - lo0, int(off[L + 1]) - lo0
                 lab = labels_all[L]
                 comm.allgather_rows(lab, ctx.bounds)
                 centers = (C_all[lo0 + lo:lo0 + hi] + ctx.mean32)[:, :ctx.d_orig].contiguous()   # _kmeans.py:1543-1546
+                disp = None
+                if strict[L]:
+                    disp = (sq[lo:hi], rt[lo:hi])
+                elif L in ext:
+                    xlo = int(off_x[len(grp) + ext.index(L)])
+                    disp = (sq[xlo:xlo + ks[L]], rt[xlo:xlo + ks[L]])
                 res[L] = KMeansResult(k=hi - lo, labels=lab, centers=centers, inertia=float(sq_h[lo:hi].sum()),
                                       n_iter=n_iter[L], counts=counts_fin[L], strict=strict[L],
-                                      csums=csums[lo0 + lo:lo0 + hi], disp=(sq[lo:hi], rt[lo:hi]) if strict[L] else None)
+                                      csums=csums[lo0 + lo:lo0 + hi], disp=disp)
         return res
 
     def _dispersion(self, ctx, Xs, labels_x, b, off_x, ks_x, C64):

@@ -82,10 +82,11 @@ def cluster_labels(X, clusters, rstate, inits=None):
         ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits)      # grouping.py:99-101
         scores = eng.cluster_scores(ctx, results)                              # grouping.py:104-108
     best_k = max(scores, key=lambda s: s[1])[0] if scores else None            # grouping.py:116 (first max)
-    return dict(clusters=clusters, labels=[r.labels.cpu().numpy() for r in results], scores=scores, best_k=best_k,
+    host = eng.to_host([r.labels for r in results] + [r.centers for r in results])      # one D2H sync for all labels and centres
+    nk = len(results)
+    return dict(clusters=clusters, labels=host[:nk], scores=scores, best_k=best_k,
                 inertia=[r.inertia for r in results], n_iter=[r.n_iter for r in results],
-                centers=[r.centers.cpu().numpy() for r in results],
-                seeds=[r.seeds for r in results])
+                centers=host[nk:], seeds=[r.seeds for r in results])
 
 
 def cluster_faces(paths, X, cluster_params):

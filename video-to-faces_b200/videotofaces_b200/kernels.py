@@ -295,7 +295,13 @@ class CudaKernels:
                 c_int(len(k_off) - 1), koff, active, two_s, ptr(acc), None, ptr(ws), stream())
 
     def cell_dispersion_ok(self, d, ks):
-        return d % 128 == 0 and d <= 1024 and max(ks) <= self.CELL_MAX_K
+        """One launch must take all labellings (at most 8, 1024 label tuples, centres within 160 KB of shared memory):
+        with more the pass over X would be repeated per group and the warp-per-row kernel is the better choice."""
+        tuples = 1
+        for k in ks:
+            tuples *= int(k)
+        return (d % 128 == 0 and d <= 1024 and max(ks) <= self.CELL_MAX_K and len(ks) <= 8 and tuples <= 1024 and
+                sum(ks) * d * 8 <= 160 * 1024)
 
     def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit):
         """int64 [2 * ktot]: per cluster slot sum |x - c|^2 * sq_unit, then sum |x - c| * rt_unit (exact integer sums of
@@ -349,19 +355,42 @@ class CudaKernels:
         nv.call('vtf_cosine_dedup', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
         return key
 
-    def cosine_dedup_tc(self, Xn, rank, world):
-        """Tensor-core dedup: split-fp16 operands (hi + lo), three MMAs per K step, fp32 accumulate."""
+    DEDUP_SCREEN_EPS = 1.0e-3          # bound of the single-MMA screen's error on a cosine similarity of unit rows
+
+    def cosine_dedup_tc(self, Xn, rank, world, thr=None, mode=None):
+        """Tensor-core dedup.  mode 'screen' (default when a threshold is given): single-MMA fp16 screen that keeps the best
+        candidates per row + exact fp32 re-evaluation, with the units whose decision at `thr` the screen cannot guarantee
+        re-swept by the split-fp16 kernel; mode 'split': split-fp16 operands (hi + lo), three MMAs per K step, everywhere.
+        `self.dedup_stats` = units re-swept by the last call."""
+        import os
         N, d = self._chk(Xn)
         P = ((N + 255) // 256) * 256
         scale = 4096.0                      # |xn| <= 1: hi keeps 11 bits, lo the next 11
+        mode = mode or os.environ.get('VTF_DEDUP_MODE') or ('screen' if thr is not None else 'split')
         hi = self.empty((P, d), torch.float16)
         lo = self.empty((P, d), torch.float16)
         key = self.empty((N,), torch.int64)
         nv.call('vtf_dedup_pack', ptr(Xn), c_i64(N), c_int(d), c_i64(P), c_f32(scale), ptr(hi), ptr(lo), stream())
         nv.call('vtf_dedup_init', ptr(key), c_i64(N), stream())
-        nv.call('vtf_cosine_dedup_tc', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), c_int(rank), c_int(world),
-                ptr(key), stream())
-        nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
+        self.dedup_stats = dict(mode=mode, units=P // 256, reswept_units=0)
+        if mode == 'split':
+            nv.call('vtf_cosine_dedup_tc', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), c_int(rank), c_int(world),
+                    ptr(key), stream())
+            nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
+            return key
+        cand = self.empty((N, 8, 2), torch.int32)
+        flags = self.zeros((P // 256 + 1,), torch.int32)         # [units] flags + [1] count
+        nv.call('vtf_dedup_screen', ptr(hi), c_i64(N), c_i64(P), c_int(d), c_int(rank), c_int(world), ptr(cand), stream())
+        nv.call('vtf_dedup_refine4', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(cand), c_f32(scale),
+                c_f32(float('nan') if thr is None else float(thr)), c_f32(self.DEDUP_SCREEN_EPS), ptr(key), ptr(flags),
+                nv.c_vp(flags.data_ptr() + 4 * (P // 256)), stream())
+        if thr is not None and int(flags[-1].item()) > 0:         # rare: rows with two neighbours in the band right above thr
+            units = torch.nonzero(flags[:-1]).flatten().to(torch.int32)
+            units = torch.flip(units, [0]).contiguous()          # largest units first
+            self.dedup_stats['reswept_units'] = int(units.numel())
+            nv.call('vtf_cosine_dedup_tc_units', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), ptr(units),
+                    c_i64(units.numel()), ptr(key), stream())
+            nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
         return key
 
     def hash_dedup(self, bits, rank, world):
