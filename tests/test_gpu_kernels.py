@@ -484,7 +484,8 @@ def test_build_cells_kernel(engine, N, ks):
 @pytest.mark.parametrize('N,d,ks', [(5000, 512, [2, 3, 4, 5, 6]), (3001, 768, [2, 5]), (1500, 1024, [3, 4, 3]), (700, 128, [48]),
                                     (20000, 512, [2, 3, 4, 5, 6, 2, 3])])
 def test_cell_dispersion_kernel(K, N, d, ks):
-    """Cell-wise dispersion (fp64 per row, exact fixed-point accumulation) against numpy fp64 and the warp-per-row kernel."""
+    """Cell-wise dispersion (fp32 differences against hi + lo centres, exact fixed-point accumulation over the rows) against
+    numpy fp64 and the all-fp64 warp-per-row kernel: per-row rounding ~1e-6, averaged down in the sums."""
     rng = np.random.default_rng(N)
     X = blobs(N, d, kc=5, seed=N, normalize=False)
     base = rng.integers(0, 6, N)
@@ -503,11 +504,11 @@ def test_cell_dispersion_kernel(K, N, d, ks):
         d2 = ((X64 - C64[off[L] + labels[L]]) ** 2).sum(1)
         np.add.at(wsq, off[L] + labels[L], d2)
         np.add.at(wrt, off[L] + labels[L], np.sqrt(d2))
-    np.testing.assert_allclose(sq, wsq, rtol=1e-11)
-    np.testing.assert_allclose(rt, wrt, rtol=1e-11)
+    np.testing.assert_allclose(sq, wsq, rtol=2e-6)
+    np.testing.assert_allclose(rt, wrt, rtol=2e-6)
     osq, ort = K.cluster_dispersion_multi(dev(X), dev(labels), 0, off, (1 << len(ks)) - 1, dev(C64))
-    np.testing.assert_allclose(sq, osq.cpu().numpy(), rtol=1e-11)
-    np.testing.assert_allclose(rt, ort.cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(sq, osq.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(rt, ort.cpu().numpy(), rtol=2e-6)
     # integers: a second run gives the same bits, whatever order the CTAs claimed their chunks in
     out2 = K.cell_dispersion(dev(X), dev(labels), 0, off, dev(C64), sq_unit, rt_unit).cpu().numpy()
     assert np.array_equal(out, out2)
@@ -533,7 +534,10 @@ def test_dedup_screen_equals_split_sweep(engine, N, d):
     for m in (m_scr, m_spl):
         got = np.nonzero(m <= thr)[0]
         assert np.array_equal(np.setdiff1d(got, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
-    np.testing.assert_allclose(m_scr, rmins, rtol=2e-6, atol=4e-7)
+    # exact fp32 dots of the kept candidates: what is left against the oracle's SGEMM is the two summation orders (d = 768:
+    # a few 1e-7 on a distance of 0.1), far inside the 1e-4 of the contract
+    np.testing.assert_allclose(m_scr, rmins, rtol=1e-5, atol=4e-7)
+    np.testing.assert_allclose(m_scr, m_spl, rtol=1e-5, atol=4e-7)
     assert (i_scr == rinds).mean() > 0.99 and (i_scr == i_spl).mean() > 0.99
 
 

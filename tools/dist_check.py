@@ -61,10 +61,15 @@ def main():
     X = plant_dupes(blobs(5000, 512, kc=4, seed=5), frac=20, seed=1)[0]
     mins, inds, idx = eng.dedup(X, 0.2)
     dist_m, lab = eng.classify(X[:3000], X[4000:4032], 0.55)
+    X2 = plant_dupes(blobs(12000, 512, kc=4, seed=6), frac=20, seed=2)[0]
+    mins2, inds2, idx2 = eng.dedup(X2, 0.2, force='tc')          # two-stage tensor-core dedup, units dealt over the ranks
     if rank == 0:
         rmins, rinds, ridx = RC.dedup_core(X, 0.2)
         check('dedup set', np.array_equal(idx, ridx))
         check('dedup mins', np.allclose(mins, rmins, rtol=1e-4, atol=3e-7))
+        rmins2, rinds2, ridx2 = RC.dedup_core(X2, 0.2)
+        check('tc dedup set', np.array_equal(idx2, ridx2))
+        check('tc dedup mins', np.allclose(mins2, rmins2, rtol=1e-4, atol=3e-7))
         _, rlab = RC.classify_core(X[:3000], X[4000:4032], 32, 0.55)
         check('classify labels', np.array_equal(lab, rlab))
         print(json.dumps(report))

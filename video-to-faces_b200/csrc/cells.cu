@@ -244,11 +244,14 @@ namespace vtf {
 // intra dispersion, davies_bouldin's distance sums; SK/cluster/_k_means_common.pyx:94-124, SK/metrics/cluster/
 // _unsupervised.py:394-399, 467-474) for several labellings in one pass.  Same chunking and grouping as cell_sums_kernel;
 // inside a cell every labelling measures against ONE centre, so a warp takes R rows of the cell at a time, keeps them in
-// registers and reads each centre element from shared memory (fp64, [slots][d]) once per R rows.  Differences, squares
-// and the lane-strided sum run in fp64, the per-row results are accumulated as 64-bit FIXED-POINT integers -- exact,
-// order-independent adds again, so the result does not depend on the scatter order, the CTA schedule or the rank count.
-// The kernel this replaces (cluster_dispersion_kernel, accumulate.cu) re-read fp64 centre rows through L1 for every row and
-// labelling: 0.16 of the HBM roofline for k = 2..6.
+// registers and reads each centre element from shared memory once per R rows.  The fp64 centre travels as two fp32 pieces
+// (hi + lo, exact to 2^-48): e = (x - hi) - lo and the lane-strided sum of e^2 run in fp32 -- B200's CUDA cores retire fp64 at
+// about 1/8 of the fp32 rate (measured: ~3e12 fp64 instructions/s in kpp_dist and in the kernel this replaces), which made
+// an all-fp64 version of this kernel fp64-bound at 1.5 ms; the reference computes the inertia in fp32 too
+// (_k_means_common.pyx:94-124).  Per row the squared distance is good to ~1e-6 relative; the per-row results are then
+// accumulated as 64-bit FIXED-POINT integers -- exact, order-independent adds, so the result does not depend on the scatter
+// order, the CTA schedule or the rank count.  The kernel this replaces (cluster_dispersion_kernel, accumulate.cu) re-read
+// fp64 centre rows through L1 for every row and labelling: 0.16 of the HBM roofline for k = 2..6.
 template <int DV, int R>
 __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const float* __restrict__ X, long long n, int d,
                                                                           const int32_t* __restrict__ labels, const CellPlan pl,
@@ -256,8 +259,9 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
                                                                           unsigned long long* __restrict__ out, unsigned int* __restrict__ bad,
                                                                           unsigned int* __restrict__ claim) {
     extern __shared__ __align__(16) unsigned char cell_smem[];
-    double* sc = reinterpret_cast<double*>(cell_smem);                                        // [n_slots][d] centres
-    long long* wacc = reinterpret_cast<long long*>(sc + (size_t)pl.n_slots * d);              // [8 warps][2][n_slots]
+    float* sc_hi = reinterpret_cast<float*>(cell_smem);                                       // [n_slots][d] centres: fp32(c)
+    float* sc_lo = sc_hi + (size_t)pl.n_slots * d;                                            // [n_slots][d]          c - fp32(c)
+    long long* wacc = reinterpret_cast<long long*>(sc_lo + (size_t)pl.n_slots * d);           // [8 warps][2][n_slots]
     unsigned int* cursor = reinterpret_cast<unsigned int*>(wacc + 8 * 2 * pl.n_slots);
     unsigned int* start = cursor + kCellKeys;
     unsigned short* keys = reinterpret_cast<unsigned short*>(start + kCellKeys);
@@ -269,7 +273,12 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long n_chunks = (n + kCellRows - 1) / kCellRows;
-    for (int i = t; i < pl.n_slots * d; i += kCellThreads) sc[i] = C64[i];
+    for (int i = t; i < pl.n_slots * d; i += kCellThreads) {
+        const double c = C64[i];
+        const float h = (float)c;
+        sc_hi[i] = h;
+        sc_lo[i] = (float)(c - (double)h);
+    }
     for (int i = t; i < 8 * 2 * pl.n_slots; i += kCellThreads) wacc[i] = 0ll;
     long long* my_sq = wacc + (size_t)warp * 2 * pl.n_slots;
     long long* my_rt = my_sq + pl.n_slots;
@@ -335,35 +344,32 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
 #pragma unroll
                     for (int v = 0; v < DV; ++v) xv[r][v] = __ldcs(xr + lane + 32 * v);
                 }
-                double acc[kCellMaxLab][R];
+                float acc[kCellMaxLab][R];
 #pragma unroll
                 for (int q = 0; q < kCellMaxLab; ++q)
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[q][r] = 0.0;
+                    for (int r = 0; r < R; ++r) acc[q][r] = 0.f;
 #pragma unroll
                 for (int v = 0; v < DV; ++v) {
-                    double x64[R][4];                            // converted once, used by every labelling
-#pragma unroll
-                    for (int r = 0; r < R; ++r) { x64[r][0] = xv[r][v].x; x64[r][1] = xv[r][v].y; x64[r][2] = xv[r][v].z; x64[r][3] = xv[r][v].w; }
 #pragma unroll
                     for (int q = 0; q < kCellMaxLab; ++q) {
                         if (q < pl.n_lab) {                      // uniform branch
-                            const double2* cr = reinterpret_cast<const double2*>(sc + (size_t)slot[q] * d) + 2 * (lane + 32 * v);
-                            const double2 c01 = cr[0], c23 = cr[1];
+                            const float4 ch = reinterpret_cast<const float4*>(sc_hi + (size_t)slot[q] * d)[lane + 32 * v];
+                            const float4 cl = reinterpret_cast<const float4*>(sc_lo + (size_t)slot[q] * d)[lane + 32 * v];
 #pragma unroll
                             for (int r = 0; r < R; ++r) {
-                                double e;
-                                e = x64[r][0] - c01.x; acc[q][r] = fma(e, e, acc[q][r]);
-                                e = x64[r][1] - c01.y; acc[q][r] = fma(e, e, acc[q][r]);
-                                e = x64[r][2] - c23.x; acc[q][r] = fma(e, e, acc[q][r]);
-                                e = x64[r][3] - c23.y; acc[q][r] = fma(e, e, acc[q][r]);
+                                float e;
+                                e = (xv[r][v].x - ch.x) - cl.x; acc[q][r] = fmaf(e, e, acc[q][r]);
+                                e = (xv[r][v].y - ch.y) - cl.y; acc[q][r] = fmaf(e, e, acc[q][r]);
+                                e = (xv[r][v].z - ch.z) - cl.z; acc[q][r] = fmaf(e, e, acc[q][r]);
+                                e = (xv[r][v].w - ch.w) - cl.w; acc[q][r] = fmaf(e, e, acc[q][r]);
                             }
                         }
                     }
                 }
                 // lane q * R + r takes the (labelling q, row r) result: square root and fixed-point conversion run on up to 32
                 // lanes at once instead of one after the other on lane 0
-                double mine = 0.0;
+                float mine = 0.f;
                 int my_slot = 0;
                 bool have = false;
 #pragma unroll
@@ -371,14 +377,14 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
                     if (q < pl.n_lab) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const double sum = warp_sum(acc[q][r]);
+                            const float sum = warp_sum(acc[q][r]);
                             if (lane == q * R + r) { mine = sum; my_slot = slot[q]; have = (j + r < en); }
                         }
                     }
                 }
                 if (have) {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(my_sq + my_slot), (unsigned long long)__double2ll_rn(mine * sq_unit));
-                    atomicAdd(reinterpret_cast<unsigned long long*>(my_rt + my_slot), (unsigned long long)__double2ll_rn(sqrt(mine) * rt_unit));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(my_sq + my_slot), (unsigned long long)__double2ll_rn((double)mine * sq_unit));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(my_rt + my_slot), (unsigned long long)__double2ll_rn((double)sqrtf(mine) * rt_unit));
                 }
             }
         }

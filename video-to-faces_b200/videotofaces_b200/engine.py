@@ -576,7 +576,10 @@ class GroupingEngine:
         error bound of the tensor-core sum."""
         K = self.K
         wx = self._wide_operand(ctx)
-        eps = 3.0 * (ctx.d // 16) * 2.0 ** -23 * self.wide_eps_scale         # one ulp per accumulating MMA
+        # Tolerance BETWEEN two scores (the candidate test compares a score with the running best): each score is off by at
+        # most one ulp per accumulating MMA (3 MMAs per K = 16 step, truncating fp32 accumulation) plus the dropped lo.lo
+        # product and the residual of the two-piece split (3 * 2^-22), all relative to |x| |c|; two scores -> twice that.
+        eps = 2.0 * (3.0 * (ctx.d // 16) * 2.0 ** -23 + 3.0 * 2.0 ** -22) * self.wide_eps_scale
         plan = cache.get(active)
         if plan is None:
             batches, cur, ncol = [], [], 0
