@@ -206,13 +206,17 @@ int vtf_cell_sums(const float* X, int64_t n, int d, const int32_t* labels, int64
                   void* stream);
 
 /* Dispersion for narrow k-ranges, organised by cells like vtf_cell_sums: out[slot] = sum_{i in slot} |x_i - C64[slot]|^2 *
- * sq_unit and out[ktot + slot] = sum |x_i - C64[slot]| * rt_unit as int64 (fp64 arithmetic per row, then exact integer
- * accumulation: the result does not depend on the order of rows, CTAs or ranks).  All n_lab labellings take part.  The
- * units must keep the totals below 2^62 (sq_unit <= 2^62 / (rows in total * max |x - c|^2)).  d % 128 == 0, d <= 1024,
- * k <= 48 per labelling.  ws: 64 + 2 * ktot * 8 bytes.  Replaces vtf_cluster_dispersion_multi on the default path.   */
+ * sq_unit and out[ktot + slot] = sum |x_i - C64[slot]| * rt_unit as int64 (zeroed here).  Labelling q measures against the
+ * centres of slots [k_off_h[q], k_off_h[q+1]) with the labels of row row_of_h[q] of the label matrix (NULL: row q): several
+ * labellings may share a label row (a fit measured against its centres AND against the means of its final labels).  Per
+ * row: e = (x - fp32(c)) - (c - fp32(c)) and the sum of e^2 in fp32 (the reference's inertia is fp32 too; ~1e-6 relative),
+ * then exact integer accumulation: the result does not depend on the order of rows, CTAs or ranks.  One launch: at most 12
+ * labellings over at most 8 distinct label rows / 1024 joint label tuples, k <= 48, centres within 160 KB; d % 128 == 0,
+ * d <= 1024.  The units must keep the totals below 2^62.  ws: 64 bytes.  Replaces vtf_cluster_dispersion_multi on the
+ * default path (SK/cluster/_k_means_common.pyx:94-124, SK/metrics/cluster/_unsupervised.py:394-399, 467-474).            */
 int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
-                        const int32_t* k_off_h, const double* C64, double sq_unit, double rt_unit, int64_t* out,
-                        uint32_t* bad, void* ws, void* stream);
+                        const int32_t* k_off_h, const int32_t* row_of_h, const double* C64, double sq_unit, double rt_unit,
+                        int64_t* out, uint32_t* bad, void* ws, void* stream);
 
 /* Cell layout of the silhouette sweep on the device (replaces a torch.unique / argsort chain): labels[n_lab][label_stride]
  * are ALL labellings of the k-range (k_h[q] clusters each, at most 4096 label tuples in total).  Occupied tuples = cells,

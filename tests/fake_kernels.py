@@ -408,11 +408,13 @@ class FakeKernels:
                 lo, hi = int(k_off[L]), int(k_off[L + 1])
                 acc[lo:hi] = torch.zeros((hi - lo, q.shape[1]), dtype=torch.int64).index_add_(0, labels_all[L, b:b + n].to(torch.int64), q)
 
-    def cell_dispersion_ok(self, d, ks):
-        return max(ks) <= self.CELL_MAX_K
+    def cell_dispersion_ok(self, d, ks, row_of=None):
+        return max(ks) <= self.CELL_MAX_K and len(ks) <= 12
 
-    def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit):
-        sq, rt = self.cluster_dispersion_multi(Xs, labels_all, b, k_off, (1 << (len(k_off) - 1)) - 1, C64_all)
+    def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit, row_of=None):
+        rows = list(range(len(k_off) - 1)) if row_of is None else list(row_of)
+        lab = labels_all[rows].contiguous()
+        sq, rt = self.cluster_dispersion_multi(Xs, lab, b, k_off, (1 << (len(k_off) - 1)) - 1, C64_all)
         return torch.cat([torch.round(sq * sq_unit), torch.round(rt * rt_unit)]).to(torch.int64)
 
     def wide_update(self, acc, inv_two_s, counts, changed, k_off, active, C_old, stats_stride):

@@ -512,6 +512,20 @@ def test_cell_dispersion_kernel(K, N, d, ks):
     # integers: a second run gives the same bits, whatever order the CTAs claimed their chunks in
     out2 = K.cell_dispersion(dev(X), dev(labels), 0, off, dev(C64), sq_unit, rt_unit).cpu().numpy()
     assert np.array_equal(out, out2)
+    # a labelling measured twice -- against its centres and against another set (the means of a tolerance-stopped fit) --
+    # shares its label row: the cell key does not grow
+    if len(ks) <= 11:
+        C2 = np.concatenate([C64, C64[off[0]:off[1]] * 0.9 + 0.01])
+        off2 = np.concatenate([off, [off[-1] + ks[0]]]).astype(np.int32)
+        rows = list(range(len(ks))) + [0]
+        assert K.cell_dispersion_ok(d, ks + [ks[0]], rows) or len(ks) >= 7
+        if K.cell_dispersion_ok(d, ks + [ks[0]], rows):
+            o3 = K.cell_dispersion(dev(X), dev(labels), 0, off2, dev(C2), sq_unit, rt_unit, rows).cpu().numpy()
+            k2 = int(off2[-1])
+            assert np.array_equal(o3[:ktot], out[:ktot]) and np.array_equal(o3[k2:k2 + ktot], out[ktot:])
+            d2 = ((X64 - C2[off2[-2] + labels[0]]) ** 2).sum(1)
+            want = np.zeros(ks[0]); np.add.at(want, labels[0], d2)
+            np.testing.assert_allclose(o3[ktot:k2] / sq_unit, want, rtol=2e-6)
 
 
 @pytest.mark.parametrize('N,d', [(9000, 512), (3000, 768), (700, 64)])
@@ -542,32 +556,31 @@ def test_dedup_screen_equals_split_sweep(engine, N, d):
 
 
 def test_dedup_screen_flags_rows_it_cannot_decide(engine):
-    """Rows with two earlier neighbours inside the screen's error band right above the threshold cannot be decided by the
-    single-MMA pass: their units are re-swept with the split operands.  Built so that the band is hit on purpose: the
-    decisions must equal the oracle's either way, and the re-sweep must have happened."""
+    """The screen keeps the four best candidates per column half and evaluates them exactly; a row is undecidable only if its
+    exact minimum is above the threshold while a FIFTH column of a half could still be below -- i.e. five or more earlier
+    rows inside the screen's error band (1e-3) right above the threshold.  Built on purpose here: the units of such rows are
+    re-swept with the split operands, and the decisions equal the oracle's."""
     K = engine.K
     rng = np.random.default_rng(3)
     N, d, thr = 4096, 512, np.float32(0.2)
     X = blobs(N, d, kc=4, seed=8)
-    for r in range(40):                                       # row i = 2000 + 50 r: two earlier rows at cos-dist thr + {2e-4, 6e-4}
+    for r in range(10):                                       # row i: six earlier rows (same column half) at cos-dist thr + {1..6}e-4
         i = 2000 + 50 * r
-        for j, delta in ((10 + 3 * r, 2e-4), (500 + 7 * r, 6e-4)):
-            c = 1.0 - (float(thr) + delta)
-            g = rng.standard_normal(d).astype(np.float64)
-            g -= g.dot(X[j].astype(np.float64)) * X[j].astype(np.float64)
+        xi = X[i].astype(np.float64)
+        for m in range(6):
+            j = 256 * m + 3 * r + m
+            c = 1.0 - (float(thr) + (m + 1) * 1e-4)
+            g = rng.standard_normal(d)
+            g -= g.dot(xi) * xi
             g /= np.linalg.norm(g)
-            if j == 10 + 3 * r:
-                base = c * X[j].astype(np.float64) + np.sqrt(1 - c * c) * g
-                X[i] = base.astype(np.float32)
-            else:                                             # rotate row j towards row i instead, so that i keeps its first neighbour
-                xi = X[i].astype(np.float64)
-                g2 = rng.standard_normal(d)
-                g2 -= g2.dot(xi) * xi
-                g2 /= np.linalg.norm(g2)
-                X[j] = (c * xi + np.sqrt(1 - c * c) * g2).astype(np.float32)
+            X[j] = (c * xi + np.sqrt(1 - c * c) * g).astype(np.float32)
     mins, inds, idx = engine.dedup(X, float(thr), force='tc')
     assert K.dedup_stats['mode'] == 'screen' and K.dedup_stats['reswept_units'] > 0
     rmins, rinds, ridx = RC.dedup_core(X, thr)
     ties = np.abs(rmins - thr) <= 1e-6
     assert np.array_equal(np.setdiff1d(idx, np.nonzero(ties)[0]), np.setdiff1d(ridx, np.nonzero(ties)[0]))
     np.testing.assert_allclose(mins, rmins, rtol=1e-4, atol=4e-7)
+    # ordinary data: nothing to re-sweep
+    X2 = plant_dupes(blobs(9000, 512, kc=4, seed=5), frac=20, seed=1)[0]
+    engine.dedup(X2, float(thr), force='tc')
+    assert K.dedup_stats['reswept_units'] == 0

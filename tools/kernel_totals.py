@@ -66,9 +66,26 @@ def main():
         if t > 0:
             rows.append((ev.key[:90], int(ev.count), t / 1e3))
     rows.sort(key=lambda r: -r[2])
+    # GPU idle time between consecutive device activities (kernels, copies, memsets) of the profiled step
+    acts = []
+    for ev in prof.events():
+        tr = getattr(ev, 'time_range', None)
+        if tr is not None and str(getattr(ev, 'device_type', '')).endswith('CUDA'):
+            acts.append((tr.start, tr.end, ev.name[:70]))
+    acts.sort()
+    gaps, idle, last_end, last_name = [], 0.0, None, None
+    for a, b, nm in acts:
+        if last_end is not None and a > last_end:
+            idle += a - last_end
+            gaps.append((a - last_end, last_name, nm))
+        if last_end is None or b > last_end:
+            last_end, last_name = b, nm
+    gaps.sort(key=lambda g: -g[0])
     print(json.dumps(dict(config=args.config, rows=N, dim=d, ks=[ks[0], ks[-1]], wall_ms=wall * 1e3, phases_ms=phases,
                           n_iter=[r.n_iter for r in res], launches=sum(r[1] for r in rows),
-                          device_ms_total=sum(r[2] for r in rows),
+                          device_ms_total=sum(r[2] for r in rows), idle_ms=idle / 1e3, n_gaps=len(gaps),
+                          gaps_over_20us=sum(1 for g in gaps if g[0] > 20), idle_in_gaps_over_20us_ms=sum(g[0] for g in gaps if g[0] > 20) / 1e3,
+                          top_gaps=[dict(us=round(g[0], 1), after=g[1], before=g[2]) for g in gaps[:25]],
                           kernels=[dict(name=n, count=c, ms=round(t, 3)) for n, c, t in rows[:args.top]])))
 
 

@@ -252,9 +252,23 @@ namespace vtf {
 // accumulated as 64-bit FIXED-POINT integers -- exact, order-independent adds, so the result does not depend on the scatter
 // order, the CTA schedule or the rank count.  The kernel this replaces (cluster_dispersion_kernel, accumulate.cu) re-read
 // fp64 centre rows through L1 for every row and labelling: 0.16 of the HBM roofline for k = 2..6.
+constexpr int kDispMaxLab = 12;      // labellings one dispersion launch measures (several may share a label row)
+
+struct DispPlan {
+    int n_key;                       // distinct label rows that make up the cell key
+    int key_row[kCellMaxLab];        // row of the label matrix
+    int key_kk[kCellMaxLab];         // its number of clusters
+    int key_mult[kCellMaxLab];       // key = sum label * mult
+    int n_lab;                       // labellings measured
+    int lab_key[kDispMaxLab];        // which key component gives the labelling's label
+    int slot0[kDispMaxLab];          // its first centre slot
+    int n_slots;
+    long long label_stride;
+};
+
 template <int DV, int R>
 __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const float* __restrict__ X, long long n, int d,
-                                                                          const int32_t* __restrict__ labels, const CellPlan pl,
+                                                                          const int32_t* __restrict__ labels, const DispPlan pl,
                                                                           const double* __restrict__ C64, double sq_unit, double rt_unit,
                                                                           unsigned long long* __restrict__ out, unsigned int* __restrict__ bad,
                                                                           unsigned int* __restrict__ claim) {
@@ -292,10 +306,10 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
         const int Rn = (int)min((long long)kCellRows, n - row0);
         for (int i = t; i < Rn; i += kCellThreads) {
             int key = 0;
-            for (int q = 0; q < pl.n_lab; ++q) {
-                int l = __ldg(labels + (long long)pl.row_of[q] * pl.label_stride + row0 + i);
-                if ((unsigned)l >= (unsigned)pl.kk[q]) { ++nbad; l = 0; }
-                key += l * pl.mult[q];
+            for (int q = 0; q < pl.n_key; ++q) {
+                int l = __ldg(labels + (long long)pl.key_row[q] * pl.label_stride + row0 + i);
+                if ((unsigned)l >= (unsigned)pl.key_kk[q]) { ++nbad; l = 0; }
+                key += l * pl.key_mult[q];
             }
             keys[i] = (unsigned short)key;
             atomicAdd(&cursor[key], 1u);
@@ -331,9 +345,10 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
         for (int s = 0; s < nseg; ++s) {
             const int key = segkey[s];
             const int st = (int)start[key], en = (int)cursor[key];
-            int slot[kCellMaxLab];                               // the cluster slot of this cell in every labelling
+            int slot[kDispMaxLab];                               // the cluster slot of this cell in every labelling
 #pragma unroll
-            for (int q = 0; q < kCellMaxLab; ++q) slot[q] = q < pl.n_lab ? pl.slot0[q] + (key / pl.mult[q]) % pl.kk[q] : 0;
+            for (int q = 0; q < kDispMaxLab; ++q)
+                slot[q] = q < pl.n_lab ? pl.slot0[q] + (key / pl.key_mult[pl.lab_key[q]]) % pl.key_kk[pl.lab_key[q]] : 0;
             // the rows of the cell, R at a time per warp
             for (int j = st + R * warp; j < en; j += R * (kCellThreads / 32)) {
                 float4 xv[R][DV];
@@ -344,15 +359,15 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
 #pragma unroll
                     for (int v = 0; v < DV; ++v) xv[r][v] = __ldcs(xr + lane + 32 * v);
                 }
-                float acc[kCellMaxLab][R];
+                float acc[kDispMaxLab][R];
 #pragma unroll
-                for (int q = 0; q < kCellMaxLab; ++q)
+                for (int q = 0; q < kDispMaxLab; ++q)
 #pragma unroll
                     for (int r = 0; r < R; ++r) acc[q][r] = 0.f;
 #pragma unroll
                 for (int v = 0; v < DV; ++v) {
 #pragma unroll
-                    for (int q = 0; q < kCellMaxLab; ++q) {
+                    for (int q = 0; q < kDispMaxLab; ++q) {
                         if (q < pl.n_lab) {                      // uniform branch
                             const float4 ch = reinterpret_cast<const float4*>(sc_hi + (size_t)slot[q] * d)[lane + 32 * v];
                             const float4 cl = reinterpret_cast<const float4*>(sc_lo + (size_t)slot[q] * d)[lane + 32 * v];
@@ -367,24 +382,29 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
                         }
                     }
                 }
-                // lane q * R + r takes the (labelling q, row r) result: square root and fixed-point conversion run on up to 32
-                // lanes at once instead of one after the other on lane 0
-                float mine = 0.f;
-                int my_slot = 0;
-                bool have = false;
+                // lane (q * R + r) % 32 takes the (labelling q, row r) result: square root and fixed-point conversion run on up
+                // to 32 lanes at once instead of one after the other on lane 0 (two rounds when there are more than 32 results)
+                float mine[2] = {0.f, 0.f};
+                int my_slot[2] = {0, 0};
+                bool have[2] = {false, false};
 #pragma unroll
-                for (int q = 0; q < kCellMaxLab; ++q) {
+                for (int q = 0; q < kDispMaxLab; ++q) {
                     if (q < pl.n_lab) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const float sum = warp_sum(acc[q][r]);
-                            if (lane == q * R + r) { mine = sum; my_slot = slot[q]; have = (j + r < en); }
+                            constexpr int dummy = 0; (void)dummy;
+                            const int idx = q * R + r;
+                            if (lane == (idx & 31)) { mine[idx >> 5] = sum; my_slot[idx >> 5] = slot[q]; have[idx >> 5] = (j + r < en); }
                         }
                     }
                 }
-                if (have) {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(my_sq + my_slot), (unsigned long long)__double2ll_rn((double)mine * sq_unit));
-                    atomicAdd(reinterpret_cast<unsigned long long*>(my_rt + my_slot), (unsigned long long)__double2ll_rn((double)sqrtf(mine) * rt_unit));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (have[h]) {
+                        atomicAdd(reinterpret_cast<unsigned long long*>(my_sq + my_slot[h]), (unsigned long long)__double2ll_rn((double)mine[h] * sq_unit));
+                        atomicAdd(reinterpret_cast<unsigned long long*>(my_rt + my_slot[h]), (unsigned long long)__double2ll_rn((double)sqrtf(mine[h]) * rt_unit));
+                    }
                 }
             }
         }
@@ -403,75 +423,64 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
 
 extern "C" {
 
-// out[0 .. ktot) = sum |x - c|^2 * sq_unit, out[ktot .. 2 ktot) = sum |x - c| * rt_unit per cluster slot, as int64 (zeroed here).
-// All n_lab labellings take part (one group of at most 8 labellings / 1024 label tuples / 48 slots per launch; d % 128 == 0,
-// d <= 1024).  The units must keep every sum below 2^62: sq_unit <= 2^62 / (n_total * max d2), likewise rt_unit.
+// out[0 .. ktot) = sum |x - c|^2 * sq_unit, out[ktot .. 2 ktot) = sum |x - c| * rt_unit per centre slot, as int64 (zeroed here).
+// Labelling q measures the rows against the centres C64[k_off[q] .. k_off[q+1]) using the labels of row row_of_h[q] of the
+// label matrix (NULL: row q) -- several labellings may share a label row (a fit measured against its centres AND against the
+// means of its final labels).  One launch: at most 12 labellings over at most 8 distinct label rows with at most 1024 joint
+// label tuples, centres within 160 KB of shared memory; d % 128 == 0, d <= 1024.  The units must keep every total below
+// 2^62: sq_unit <= 2^62 / (rows in total * max |x - c|^2), likewise rt_unit.
 int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels, int64_t label_stride, int n_lab,
-                        const int32_t* k_off_h, const double* C64, double sq_unit, double rt_unit, int64_t* out, uint32_t* bad,
-                        void* ws, void* stream) {
+                        const int32_t* k_off_h, const int32_t* row_of_h, const double* C64, double sq_unit, double rt_unit,
+                        int64_t* out, uint32_t* bad, void* ws, void* stream) {
     VTF_REQUIRE(X && labels && k_off_h && C64 && out && ws && n >= 0 && d > 0 && d % 128 == 0 && d <= 1024 && n_lab > 0 &&
-                    n_lab <= kMaxSeg && label_stride >= n && k_off_h[0] == 0 && sq_unit > 0.0 && rt_unit > 0.0,
-                "vtf_cell_dispersion (d % 128 == 0, d <= 1024)");
+                    n_lab <= kDispMaxLab && label_stride >= n && k_off_h[0] == 0 && sq_unit > 0.0 && rt_unit > 0.0,
+                "vtf_cell_dispersion (d % 128 == 0, d <= 1024, at most 12 labellings)");
     cudaStream_t st = (cudaStream_t)stream;
     const int ktot = k_off_h[n_lab];
     VTF_CUDA(cudaMemsetAsync(out, 0, (size_t)2 * ktot * sizeof(int64_t), st), "vtf_cell_dispersion/zero");
     if (bad) VTF_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st), "vtf_cell_dispersion/zero");
     if (n == 0) return VTF_OK;
-    int L = 0, launch = 0;
-    while (L < n_lab) {
-        CellPlan pl = {};
-        const int L0 = L;
-        long long keys = 1;
-        while (L < n_lab) {
-            const int k = k_off_h[L + 1] - k_off_h[L];
-            VTF_REQUIRE(k > 0 && k <= kCellMaxSlots, "vtf_cell_dispersion: 1 <= k <= 48 per labelling");
-            const size_t need = (size_t)(k_off_h[L + 1] - k_off_h[L0]) * d * sizeof(double);
-            if (pl.n_lab > 0 && (pl.n_lab >= kCellMaxLab || keys * k > kCellKeys || need > 160 * 1024)) break;
-            VTF_REQUIRE(need <= 200 * 1024, "vtf_cell_dispersion: k * d too large");
-            pl.row_of[pl.n_lab] = L;
-            pl.slot0[pl.n_lab] = k_off_h[L] - k_off_h[L0];
-            pl.kk[pl.n_lab] = k;
-            pl.mult[pl.n_lab] = (int)keys;
+    DispPlan pl = {};
+    long long keys = 1;
+    for (int q = 0; q < n_lab; ++q) {
+        const int k = k_off_h[q + 1] - k_off_h[q];
+        const int row = row_of_h ? row_of_h[q] : q;
+        VTF_REQUIRE(k > 0 && k <= kCellMaxSlots && row >= 0, "vtf_cell_dispersion: 1 <= k <= 48 per labelling");
+        int kq = -1;
+        for (int c = 0; c < pl.n_key; ++c) if (pl.key_row[c] == row) kq = c;
+        if (kq < 0) {
+            VTF_REQUIRE(pl.n_key < kCellMaxLab && keys * k <= kCellKeys, "vtf_cell_dispersion: more than 8 label rows or 1024 label tuples");
+            kq = pl.n_key++;
+            pl.key_row[kq] = row; pl.key_kk[kq] = k; pl.key_mult[kq] = (int)keys;
             keys *= k;
-            ++pl.n_lab;
-            ++L;
         }
-        pl.n_slots = k_off_h[L] - k_off_h[L0];
-        pl.label_stride = label_stride;
-        const size_t smem = (size_t)pl.n_slots * d * sizeof(double) + (size_t)8 * 2 * pl.n_slots * sizeof(long long) +
-                            2 * kCellKeys * sizeof(unsigned int) + 2 * kCellRows * sizeof(unsigned short) + kCellKeys * sizeof(unsigned short);
-        VTF_REQUIRE(launch < 16, "vtf_cell_dispersion: too many groups");
-        unsigned int* claim = reinterpret_cast<unsigned int*>(ws) + launch;
-        VTF_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), st), "vtf_cell_dispersion/claim");
-        const long long chunks = (n + kCellRows - 1) / kCellRows;
-        const unsigned grid = (unsigned)max(1ll, min(chunks, (long long)num_sms()));
-        // sq and rt of this group's slots live at out[k_off[L0] ..] and out[ktot + k_off[L0] ..]: the kernel writes [2][n_slots]
-        // contiguously, so groups other than the only one go through a scratch area in ws and are scattered by a copy
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(out);
-        const bool whole = (L0 == 0 && L == n_lab);
-        unsigned long long* tmp = whole ? dst : reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + 64) + (size_t)2 * k_off_h[L0];
-        if (!whole) VTF_CUDA(cudaMemsetAsync(tmp, 0, (size_t)2 * pl.n_slots * sizeof(int64_t), st), "vtf_cell_dispersion/tmp");
+        VTF_REQUIRE(pl.key_kk[kq] == k, "vtf_cell_dispersion: labellings that share a label row must have the same k");
+        pl.lab_key[q] = kq;
+        pl.slot0[q] = k_off_h[q];
+    }
+    pl.n_lab = n_lab;
+    pl.n_slots = ktot;
+    pl.label_stride = label_stride;
+    VTF_REQUIRE((size_t)ktot * d * sizeof(double) <= 160 * 1024, "vtf_cell_dispersion: centres exceed 160 KB");
+    const size_t smem = (size_t)ktot * d * sizeof(double) + (size_t)8 * 2 * ktot * sizeof(long long) + 2 * kCellKeys * sizeof(unsigned int) +
+                        2 * kCellRows * sizeof(unsigned short) + kCellKeys * sizeof(unsigned short);
+    unsigned int* claim = reinterpret_cast<unsigned int*>(ws);
+    VTF_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), st), "vtf_cell_dispersion/claim");
+    const long long chunks = (n + kCellRows - 1) / kCellRows;
+    const unsigned grid = (unsigned)max(1ll, min(chunks, (long long)num_sms()));
 #define VTF_CD_CASE(DVv, Rv)                                                                                                        \
     case DVv:                                                                                                                       \
         VTF_CUDA(cudaFuncSetAttribute(cell_dispersion_kernel<DVv, Rv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),     \
                  "vtf_cell_dispersion/smem");                                                                                       \
-        VTF_LAUNCH((cell_dispersion_kernel<DVv, Rv>), grid, kCellThreads, smem, stream, X, (long long)n, d, labels, pl,             \
-                   C64 + (size_t)k_off_h[L0] * d, sq_unit, rt_unit, tmp, bad, claim);                                               \
+        VTF_LAUNCH((cell_dispersion_kernel<DVv, Rv>), grid, kCellThreads, smem, stream, X, (long long)n, d, labels, pl, C64, sq_unit, \
+                   rt_unit, reinterpret_cast<unsigned long long*>(out), bad, claim);                                                \
         break;
-        switch (d / 128) {
-            VTF_CD_CASE(1, 4) VTF_CD_CASE(2, 4) VTF_CD_CASE(3, 4) VTF_CD_CASE(4, 4)
-            VTF_CD_CASE(5, 2) VTF_CD_CASE(6, 2) VTF_CD_CASE(7, 2) VTF_CD_CASE(8, 2)
-        }
-#undef VTF_CD_CASE
-        VTF_CHECK_LAST("vtf_cell_dispersion");
-        if (!whole) {
-            VTF_CUDA(cudaMemcpyAsync(out + k_off_h[L0], tmp, (size_t)pl.n_slots * sizeof(int64_t), cudaMemcpyDeviceToDevice, st),
-                     "vtf_cell_dispersion/copy");
-            VTF_CUDA(cudaMemcpyAsync(out + ktot + k_off_h[L0], tmp + pl.n_slots, (size_t)pl.n_slots * sizeof(int64_t),
-                                     cudaMemcpyDeviceToDevice, st), "vtf_cell_dispersion/copy");
-        }
-        ++launch;
+    switch (d / 128) {
+        VTF_CD_CASE(1, 4) VTF_CD_CASE(2, 4) VTF_CD_CASE(3, 4) VTF_CD_CASE(4, 4)
+        VTF_CD_CASE(5, 2) VTF_CD_CASE(6, 2) VTF_CD_CASE(7, 2) VTF_CD_CASE(8, 2)
     }
+#undef VTF_CD_CASE
+    VTF_CHECK_LAST("vtf_cell_dispersion");
     return VTF_OK;
 }
 

@@ -57,8 +57,8 @@ SIGNATURES = {
     'vtf_wide_update': (c_int, [c_vp, ctypes.c_double, c_vp, c_vp, c_int, c_vp, ctypes.c_uint32, c_int, c_vp, c_vp, c_vp, c_int,
                                 c_vp]),
     'vtf_cell_sums': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, ctypes.c_uint32, ctypes.c_double, c_vp, c_vp, c_vp, c_vp]),
-    'vtf_cell_dispersion': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
-                                    c_vp, c_vp]),
+    'vtf_cell_dispersion': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, c_vp,
+                                    c_vp, c_vp, c_vp]),
     'vtf_cosine_classify': (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     'vtf_dedup_init': (c_int, [c_vp, c_i64, c_vp]),
     'vtf_cosine_dedup': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),

@@ -498,14 +498,14 @@ class GroupingEngine:
         # against the fp64 means of its final labels (a "virtual" labelling with the same label row).
         ext = [L for L in range(nL) if not strict[L] and csums[L] is not None]
         C64 = C_all.to(torch.float64)
-        labels_x, off_x = labels_all, off
+        off_x = off
         if ext:
-            labels_x = torch.cat([labels_all, labels_all[ext]]).contiguous()
             means = [csums[L] / counts_fin[L].to(torch.float64).clamp_min(1).unsqueeze(1) for L in ext]
             C64 = torch.cat([C64] + means).contiguous()
             off_x = np.concatenate([off, off[-1] + np.cumsum([ks[L] for L in ext])]).astype(np.int32)
         kx = int(off_x[-1])
-        sq, rt = self._dispersion(ctx, Xs, labels_x, b, off_x, [ks[L] for L in range(nL)] + [ks[L] for L in ext], C64)
+        sq, rt = self._dispersion(ctx, Xs, labels_all, b, off_x, [ks[L] for L in range(nL)] + [ks[L] for L in ext], C64,
+                                  list(range(nL)) + ext)
         sq_h = sq.cpu().numpy()
         res = []
         for L in range(nL):
@@ -710,15 +710,14 @@ class GroupingEngine:
             # every labelling against its centres (inertia; for 'labels unchanged' fits also CH's intra dispersion and DB's
             # distance sums); tolerance-stopped fits a second time against the fp64 means of their final labels
             ext = [L for L in grp if not strict[L]][:32 - len(grp)]
-            labels_x = labels_all[g0:g1]
             C64 = C64_all[lo0:hi0]
             off_x = (off[g0:g1 + 1] - off[g0]).astype(np.int32)
             if ext:
-                labels_x = torch.cat([labels_x, labels_all[ext]]).contiguous()
                 means = [csums[int(off[L]):int(off[L + 1])] / counts_fin[L].to(torch.float64).clamp_min(1).unsqueeze(1) for L in ext]
                 C64 = torch.cat([C64] + means).contiguous()
                 off_x = np.concatenate([off_x, off_x[-1] + np.cumsum([ks[L] for L in ext])]).astype(np.int32)
-            sq, rt = self._dispersion(ctx, Xs, labels_x, b, off_x, [ks[L] for L in grp] + [ks[L] for L in ext], C64.contiguous())
+            sq, rt = self._dispersion(ctx, Xs, labels_all, b, off_x, [ks[L] for L in grp] + [ks[L] for L in ext], C64.contiguous(),
+                                      list(grp) + ext)
             sq_h = sq.cpu().numpy()
             for L in grp:
                 lo, hi = int(off[L]) - lo0, int(off[L + 1]) - lo0
@@ -736,21 +735,22 @@ class GroupingEngine:
                                       csums=csums[lo0 + lo:lo0 + hi], disp=disp)
         return res
 
-    def _dispersion(self, ctx, Xs, labels_x, b, off_x, ks_x, C64):
-        """(sq, rt) fp64 [sum k], all-reduced: per cluster the sums of |x - c|^2 and |x - c| over this fit context's rows.
-        Narrow k-ranges run cell-wise with exact fixed-point accumulation (csrc/cells.cu); the units follow from the largest
-        squared row norm of the centred matrix (centres are means of rows, so |x - c|^2 <= 4 max |x|^2)."""
+    def _dispersion(self, ctx, Xs, labels_all, b, off_x, ks_x, C64, row_of):
+        """(sq, rt) fp64 [sum k], all-reduced: per centre slot the sums of |x - c|^2 and |x - c| over this fit context's rows;
+        labelling q measures against centre slots [off_x[q], off_x[q+1]) with label row row_of[q] of labels_all (rows may be
+        shared).  Narrow k-ranges run cell-wise with exact fixed-point accumulation (csrc/cells.cu); the units follow from
+        the largest squared row norm of the centred matrix (centres are means of rows, so |x - c|^2 <= 4 max |x|^2)."""
         K, comm = self.K, self.comm
         kx = int(off_x[-1])
         max_sqn = getattr(ctx, 'max_sqn', None)
-        if (max_sqn and max_sqn > 0.0 and hasattr(K, 'cell_dispersion') and K.cell_dispersion_ok(ctx.d, ks_x) and
-                labels_x.shape[0] <= 32):
+        if max_sqn and max_sqn > 0.0 and hasattr(K, 'cell_dispersion') and K.cell_dispersion_ok(ctx.d, ks_x, row_of):
             bound = 4.5 * max_sqn
             sq_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (max(ctx.N, 2) * bound)))
             rt_unit = 2.0 ** math.floor(math.log2(2.0 ** 62 / (max(ctx.N, 2) * math.sqrt(bound))))
-            out = K.cell_dispersion(Xs, labels_x, b, off_x, C64, sq_unit, rt_unit)
+            out = K.cell_dispersion(Xs, labels_all, b, off_x, C64, sq_unit, rt_unit, row_of)
             comm.allreduce_sum(out)                                            # integers: exact in any order
             return out[:kx].to(torch.float64) / sq_unit, out[kx:].to(torch.float64) / rt_unit
+        labels_x = labels_all[row_of].contiguous()
         sq, rt = K.cluster_dispersion_multi(Xs, labels_x, b, off_x, (1 << labels_x.shape[0]) - 1, C64)
         both = torch.cat([sq, rt])
         comm.allreduce_sum(both)

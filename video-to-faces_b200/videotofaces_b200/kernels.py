@@ -294,25 +294,30 @@ class CudaKernels:
         nv.call('vtf_cell_sums', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
                 c_int(len(k_off) - 1), koff, active, two_s, ptr(acc), None, ptr(ws), stream())
 
-    def cell_dispersion_ok(self, d, ks):
-        """One launch must take all labellings (at most 8, 1024 label tuples, centres within 160 KB of shared memory):
-        with more the pass over X would be repeated per group and the warp-per-row kernel is the better choice."""
-        tuples = 1
-        for k in ks:
-            tuples *= int(k)
-        return (d % 128 == 0 and d <= 1024 and max(ks) <= self.CELL_MAX_K and len(ks) <= 8 and tuples <= 1024 and
+    def cell_dispersion_ok(self, d, ks, row_of=None):
+        """One launch takes all labellings: at most 12 of them over at most 8 distinct label rows with at most 1024 joint
+        label tuples, k <= 48, centres within 160 KB of shared memory.  Beyond that the warp-per-row kernel is used."""
+        rows = list(range(len(ks))) if row_of is None else list(row_of)
+        seen, tuples = {}, 1
+        for k, r in zip(ks, rows):
+            if r not in seen:
+                seen[r] = k
+                tuples *= int(k)
+        return (d % 128 == 0 and d <= 1024 and max(ks) <= self.CELL_MAX_K and len(ks) <= 12 and len(seen) <= 8 and tuples <= 1024 and
                 sum(ks) * d * 8 <= 160 * 1024)
 
-    def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit):
-        """int64 [2 * ktot]: per cluster slot sum |x - c|^2 * sq_unit, then sum |x - c| * rt_unit (exact integer sums of
-        per-row fp64 values: add across ranks as integers, then divide by the units)."""
+    def cell_dispersion(self, Xs, labels_all, b, k_off, C64_all, sq_unit, rt_unit, row_of=None):
+        """int64 [2 * ktot]: per centre slot sum |x - c|^2 * sq_unit, then sum |x - c| * rt_unit (exact integer sums of per-row
+        values: add across ranks as integers, then divide by the units).  row_of[q] = label row labelling q reads."""
+        import numpy as np
         n, d = self._chk(Xs)
         keep, koff = self._koff(k_off)
+        keep2, rof = (None, None) if row_of is None else self._koff(np.asarray(row_of, dtype=np.int32))
         ktot = int(k_off[-1])
         out = self.empty((2 * ktot,), torch.int64)
-        ws = self._workspace(64 + 16 * ktot)
+        ws = self._workspace(64)
         nv.call('vtf_cell_dispersion', ptr(Xs), c_i64(n), c_int(d), nv.c_vp(labels_all.data_ptr() + 4 * b), c_i64(labels_all.shape[1]),
-                c_int(len(k_off) - 1), koff, ptr(C64_all), sq_unit, rt_unit, ptr(out), None, ptr(ws), stream())
+                c_int(len(k_off) - 1), koff, rof, ptr(C64_all), sq_unit, rt_unit, ptr(out), None, ptr(ws), stream())
         return out
 
     BUILD_CELLS_MAX_KEYS = 4096
