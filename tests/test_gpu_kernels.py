@@ -482,7 +482,7 @@ def test_build_cells_kernel(engine, N, ks):
 
 
 @pytest.mark.parametrize('N,d,ks', [(5000, 512, [2, 3, 4, 5, 6]), (3001, 768, [2, 5]), (1500, 1024, [3, 4, 3]), (700, 128, [48]),
-                                    (20000, 512, [2, 3, 4, 5, 6, 2, 3])])
+                                    (20000, 512, [2, 3, 4, 5, 2, 3])])
 def test_cell_dispersion_kernel(K, N, d, ks):
     """Cell-wise dispersion (fp32 differences against hi + lo centres, exact fixed-point accumulation over the rows) against
     numpy fp64 and the all-fp64 warp-per-row kernel: per-row rounding ~1e-6, averaged down in the sums."""
