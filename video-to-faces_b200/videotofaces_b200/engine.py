@@ -858,8 +858,10 @@ class GroupingEngine:
                 both = torch.cat([sq, rt])
                 comm.allreduce_sum(both)
             ktot = int(off[-1])
-            sq_h, rt_h = both[:ktot].cpu().numpy(), both[ktot:].cpu().numpy()
-            means_h, cnt_h, mean_h = means.cpu().numpy(), cnt_all.cpu().numpy(), gmean.cpu().numpy()
+            d_ = means.shape[1]
+            flat = torch.cat([both.to(torch.float64), cnt_all, gmean.to(torch.float64), means.reshape(-1)]).cpu().numpy()   # one D2H
+            sq_h, rt_h, cnt_h = flat[:ktot], flat[ktot:2 * ktot], flat[2 * ktot:3 * ktot]
+            mean_h, means_h = flat[3 * ktot:3 * ktot + d_], flat[3 * ktot + d_:].reshape(ktot, d_)
             for L, j in enumerate(grp):
                 lo, hi = int(off[L]), int(off[L + 1])
                 present = cnt_h[lo:hi] > 0
