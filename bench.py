@@ -466,6 +466,7 @@ def run_config(cfg, args, env, steps, warmup, headline):
             out['mins'], out['inds'], out['idx'] = eng.dedup(X, cfg['dup_thr'])
             X = eng.delete_rows(X, out['idx']) if out['idx'].size else X
             out['rows_after_dedup'] = int(X.shape[0])
+        out['X'] = X
         if kind == 'dedup_classify':
             out['dist'], out['lab'] = eng.classify(X, Rd, cfg['oth_thr'])
         else:
@@ -572,6 +573,7 @@ def run_config(cfg, args, env, steps, warmup, headline):
 
     # ---- size-independent properties at full size
     props = {}
+    X_step = out.pop('X')
     if 'res' in out:
         inert = rec['inertia']
         props.update(inertia_decreasing=bool(all(a > b for a, b in zip(inert, inert[1:]))),
@@ -582,6 +584,24 @@ def run_config(cfg, args, env, steps, warmup, headline):
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             props['labels_equal_on_all_ranks'] = bool(torch.equal(lo, hi))
+        if world > 1:
+            # the sharded path against every rank computing a 16 384-row sample alone (same kernels, no exchange): labels
+            # identical, scores equal -- in the full and in the symmetric (benchmarked) form of the sweep
+            Xs_d = X_step[:min(16384, X_step.shape[0])].contiguous()
+            worst = 0.0
+            same_labels = True
+            for sym in (False, True):
+                eng.sym = sym
+                try:
+                    r_sh = cluster_labels(Xs_d, cfg['ks'][:5], 0)
+                    with eng.solo_if(True):
+                        r_so = cluster_labels(Xs_d, cfg['ks'][:5], 0)
+                finally:
+                    eng.sym = None
+                same_labels = same_labels and all(np.array_equal(a, b) for a, b in zip(r_sh['labels'], r_so['labels']))
+                worst = max(worst, max(_rel(a[c], b[c]) for a, b in zip(r_sh['scores'], r_so['scores']) for c in (1, 2, 3)))
+            props.update(sharded_sample_labels_equal_unsharded=bool(same_labels), sharded_sample_scores_rel=worst,
+                         sharded_sample_ok=bool(same_labels and worst <= 1e-5))
         if cfg['name'] == 'c3' and N == 1_000_000 and d == 512:
             rel = [_rel(a, b) for a, b in zip(inert, KNOWN_1M_512['inertia'])]
             props.update(known_answer_inertia_rel=rel, known_answer_n_iter_equal=bool(rec['n_iter'] == KNOWN_1M_512['n_iter']),
@@ -681,7 +701,7 @@ def run_config(cfg, args, env, steps, warmup, headline):
             scaling=ex, info=info_c)
     if headline:
         rec['clocks'] = sampler.summary()
-    del Xd
+    del Xd, X_step
     torch.cuda.empty_cache()
     return rec
 

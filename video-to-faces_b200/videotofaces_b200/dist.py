@@ -46,6 +46,12 @@ class Comm:
             self._dist.broadcast_object_list(box, src=src, group=self.group)
         return box
 
+    def broadcast(self, t, src=0):
+        """Every rank's tensor `t` takes rank `src`'s contents."""
+        if self.active:
+            self._dist.broadcast(t, src=self._global(src), group=self.group)
+        return t
+
     def allreduce_min(self, t):
         if self.active:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)

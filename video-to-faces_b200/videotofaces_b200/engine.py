@@ -929,7 +929,13 @@ class GroupingEngine:
             tuples = min(tuples * int(k), 1 << 40)
         if hasattr(self.K, 'build_cells') and tuples <= self.K.BUILD_CELLS_MAX_KEYS and len(ks) <= 32:
             # narrow k-ranges (k = 2..6: 720 tuples): keys, histogram, layout and scatter in three launches, no sort
-            return self.K.build_cells(torch.stack([l.to(torch.int32) for l in labels_list]).contiguous(), [int(k) for k in ks])
+            perm, chunk_cell, c2c, G, P = self.K.build_cells(torch.stack([l.to(torch.int32) for l in labels_list]).contiguous(),
+                                                            [int(k) for k in ks])
+            # G, P, chunk_cell and c2c are functions of the label histogram (the same on every rank); the ORDER of the rows
+            # inside a cell comes from atomics and differs from rank to rank -- and the ranks must agree on it: each one sweeps
+            # a share of the positions and their cell sums are added position by position.  Rank 0's layout is the layout.
+            self.comm.broadcast(perm, src=0)
+            return perm, chunk_cell, c2c, G, P
         key = torch.zeros(N, dtype=torch.int64, device=dev)
         span = 1
         for lab, k in zip(labels_list, ks):
