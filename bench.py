@@ -380,7 +380,7 @@ def phase_table(cfg, N, d, phases_ms, pk, world, info):
 def committed_traffic(cfg, N, d, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel -- NOT measured in this run: read from the
     committed `ncu --set full` capture of the same shape, when there is one."""
-    name = {'cluster': 'sweep', 'dedup_cluster': 'sweep', 'dedup_classify': 'dedup'}[cfg['kind']]
+    name = {'cluster': 'sweep', 'dedup_cluster': 'sweep', 'dedup_classify': 'dedup_screen'}[cfg['kind']]
     for rnd in ('r02', 'r01'):
         try:
             with open(osp.join(ROOT, 'profiles', '%s_%s_ncu_summary.json' % (rnd, name))) as f:

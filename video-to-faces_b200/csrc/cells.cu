@@ -266,8 +266,11 @@ struct DispPlan {
     long long label_stride;
 };
 
+constexpr int kDispThreads = 512;    // 16 warps share one shared-memory copy of the centres (2 rows per warp at a time: <= 128 registers)
+constexpr int kDispWarps = kDispThreads / 32;
+
 template <int DV, int R>
-__global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const float* __restrict__ X, long long n, int d,
+__global__ void __launch_bounds__(kDispThreads, 1) cell_dispersion_kernel(const float* __restrict__ X, long long n, int d,
                                                                           const int32_t* __restrict__ labels, const DispPlan pl,
                                                                           const double* __restrict__ C64, double sq_unit, double rt_unit,
                                                                           unsigned long long* __restrict__ out, unsigned int* __restrict__ bad,
@@ -275,36 +278,36 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
     extern __shared__ __align__(16) unsigned char cell_smem[];
     float* sc_hi = reinterpret_cast<float*>(cell_smem);                                       // [n_slots][d] centres: fp32(c)
     float* sc_lo = sc_hi + (size_t)pl.n_slots * d;                                            // [n_slots][d]          c - fp32(c)
-    long long* wacc = reinterpret_cast<long long*>(sc_lo + (size_t)pl.n_slots * d);           // [8 warps][2][n_slots]
-    unsigned int* cursor = reinterpret_cast<unsigned int*>(wacc + 8 * 2 * pl.n_slots);
+    long long* wacc = reinterpret_cast<long long*>(sc_lo + (size_t)pl.n_slots * d);           // [16 warps][2][n_slots]
+    unsigned int* cursor = reinterpret_cast<unsigned int*>(wacc + kDispWarps * 2 * pl.n_slots);
     unsigned int* start = cursor + kCellKeys;
     unsigned short* keys = reinterpret_cast<unsigned short*>(start + kCellKeys);
     unsigned short* order = keys + kCellRows;
     unsigned short* segkey = order + kCellRows;
-    __shared__ unsigned int warp_tot[kCellThreads / 32];
+    __shared__ unsigned int warp_tot[kDispWarps];
     __shared__ int s_nseg;
     __shared__ unsigned int s_chunk;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long n_chunks = (n + kCellRows - 1) / kCellRows;
-    for (int i = t; i < pl.n_slots * d; i += kCellThreads) {
+    for (int i = t; i < pl.n_slots * d; i += kDispThreads) {
         const double c = C64[i];
         const float h = (float)c;
         sc_hi[i] = h;
         sc_lo[i] = (float)(c - (double)h);
     }
-    for (int i = t; i < 8 * 2 * pl.n_slots; i += kCellThreads) wacc[i] = 0ll;
+    for (int i = t; i < kDispWarps * 2 * pl.n_slots; i += kDispThreads) wacc[i] = 0ll;
     long long* my_sq = wacc + (size_t)warp * 2 * pl.n_slots;
     long long* my_rt = my_sq + pl.n_slots;
     unsigned int nbad = 0;
     for (;;) {
         if (t == 0) s_chunk = atomicAdd(claim, 1u);
-        for (int i = t; i < kCellKeys; i += kCellThreads) cursor[i] = 0u;
+        for (int i = t; i < kCellKeys; i += kDispThreads) cursor[i] = 0u;
         __syncthreads();
         if ((long long)s_chunk >= n_chunks) break;
         const long long row0 = (long long)s_chunk * kCellRows;
         const int Rn = (int)min((long long)kCellRows, n - row0);
-        for (int i = t; i < Rn; i += kCellThreads) {
+        for (int i = t; i < Rn; i += kDispThreads) {
             int key = 0;
             for (int q = 0; q < pl.n_key; ++q) {
                 int l = __ldg(labels + (long long)pl.key_row[q] * pl.label_stride + row0 + i);
@@ -315,10 +318,11 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
             atomicAdd(&cursor[key], 1u);
         }
         __syncthreads();
-        unsigned int c4[4];
+        constexpr int kBins = kCellKeys / kDispThreads;      // histogram bins per thread in the scan
+        unsigned int c4[kBins];
         unsigned int local = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { c4[j] = cursor[4 * t + j]; local += c4[j] + (c4[j] ? 0x10000u : 0u); }
+        for (int j = 0; j < kBins; ++j) { c4[j] = cursor[kBins * t + j]; local += c4[j] + (c4[j] ? 0x10000u : 0u); }
         unsigned int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
@@ -326,19 +330,19 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
         __syncthreads();
         unsigned int base = incl - local;
         for (int w = 0; w < warp; ++w) base += warp_tot[w];
-        if (t == kCellThreads - 1) s_nseg = (int)((base + local) >> 16);
+        if (t == kDispThreads - 1) s_nseg = (int)((base + local) >> 16);
         {
             unsigned int pos = base & 0xffffu, seg = base >> 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                start[4 * t + j] = pos;
-                cursor[4 * t + j] = pos;
-                if (c4[j]) segkey[seg++] = (unsigned short)(4 * t + j);
+            for (int j = 0; j < kBins; ++j) {
+                start[kBins * t + j] = pos;
+                cursor[kBins * t + j] = pos;
+                if (c4[j]) segkey[seg++] = (unsigned short)(kBins * t + j);
                 pos += c4[j];
             }
         }
         __syncthreads();
-        for (int i = t; i < Rn; i += kCellThreads) order[atomicAdd(&cursor[keys[i]], 1u)] = (unsigned short)i;
+        for (int i = t; i < Rn; i += kDispThreads) order[atomicAdd(&cursor[keys[i]], 1u)] = (unsigned short)i;
         __syncthreads();
 
         const int nseg = s_nseg;
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
             for (int q = 0; q < kDispMaxLab; ++q)
                 slot[q] = q < pl.n_lab ? pl.slot0[q] + (key / pl.key_mult[pl.lab_key[q]]) % pl.key_kk[pl.lab_key[q]] : 0;
             // the rows of the cell, R at a time per warp
-            for (int j = st + R * warp; j < en; j += R * (kCellThreads / 32)) {
+            for (int j = st + R * warp; j < en; j += R * kDispWarps) {
                 float4 xv[R][DV];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -412,9 +416,9 @@ __global__ void __launch_bounds__(kCellThreads, 1) cell_dispersion_kernel(const 
     }
     if (nbad && bad) atomicAdd(bad, nbad);
     __syncthreads();
-    for (int i = t; i < 2 * pl.n_slots; i += kCellThreads) {
+    for (int i = t; i < 2 * pl.n_slots; i += kDispThreads) {
         long long v = 0;
-        for (int w = 0; w < 8; ++w) v += wacc[(size_t)w * 2 * pl.n_slots + i];
+        for (int w = 0; w < kDispWarps; ++w) v += wacc[(size_t)w * 2 * pl.n_slots + i];
         if (v) atomicAdd(out + i, (unsigned long long)v);
     }
 }
@@ -462,7 +466,7 @@ int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels,
     pl.n_slots = ktot;
     pl.label_stride = label_stride;
     VTF_REQUIRE((size_t)ktot * d * sizeof(double) <= 160 * 1024, "vtf_cell_dispersion: centres exceed 160 KB");
-    const size_t smem = (size_t)ktot * d * sizeof(double) + (size_t)8 * 2 * ktot * sizeof(long long) + 2 * kCellKeys * sizeof(unsigned int) +
+    const size_t smem = (size_t)ktot * d * sizeof(double) + (size_t)kDispWarps * 2 * ktot * sizeof(long long) + 2 * kCellKeys * sizeof(unsigned int) +
                         2 * kCellRows * sizeof(unsigned short) + kCellKeys * sizeof(unsigned short);
     unsigned int* claim = reinterpret_cast<unsigned int*>(ws);
     VTF_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), st), "vtf_cell_dispersion/claim");
@@ -472,12 +476,12 @@ int vtf_cell_dispersion(const float* X, int64_t n, int d, const int32_t* labels,
     case DVv:                                                                                                                       \
         VTF_CUDA(cudaFuncSetAttribute(cell_dispersion_kernel<DVv, Rv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),     \
                  "vtf_cell_dispersion/smem");                                                                                       \
-        VTF_LAUNCH((cell_dispersion_kernel<DVv, Rv>), grid, kCellThreads, smem, stream, X, (long long)n, d, labels, pl, C64, sq_unit, \
+        VTF_LAUNCH((cell_dispersion_kernel<DVv, Rv>), grid, kDispThreads, smem, stream, X, (long long)n, d, labels, pl, C64, sq_unit, \
                    rt_unit, reinterpret_cast<unsigned long long*>(out), bad, claim);                                                \
         break;
     switch (d / 128) {
-        VTF_CD_CASE(1, 4) VTF_CD_CASE(2, 4) VTF_CD_CASE(3, 4) VTF_CD_CASE(4, 4)
-        VTF_CD_CASE(5, 2) VTF_CD_CASE(6, 2) VTF_CD_CASE(7, 2) VTF_CD_CASE(8, 2)
+        VTF_CD_CASE(1, 2) VTF_CD_CASE(2, 2) VTF_CD_CASE(3, 2) VTF_CD_CASE(4, 2)
+        VTF_CD_CASE(5, 1) VTF_CD_CASE(6, 1) VTF_CD_CASE(7, 1) VTF_CD_CASE(8, 1)
     }
 #undef VTF_CD_CASE
     VTF_CHECK_LAST("vtf_cell_dispersion");
