@@ -50,6 +50,12 @@ int vtf_normalize_rows(const float* X, int64_t N, int d, float* Xn, void* stream
 size_t vtf_col_stats_ws_bytes(int d);
 int vtf_col_stats(const float* X, int64_t N, int d, double* col_sum, double* col_sumsq,
                   void* ws, void* stream);
+/* Encoder hand-off: Xn = normalize(X) (as vtf_normalize_rows; FaceNet's own last step,
+ * encoders/facenet.py:153) AND the column sums / sums of squares of Xn (fp64, as vtf_col_stats) in one pass over
+ * un-normalised embeddings.  d % 128 == 0, d <= 1024.  ws: vtf_normalize_col_stats_ws_bytes(d).                */
+size_t vtf_normalize_col_stats_ws_bytes(int d);
+int vtf_normalize_col_stats(const float* X, int64_t N, int d, float* Xn, double* col_sum, double* col_sumsq, void* ws,
+                            void* stream);
 /* Xc = X - mean (fp32), SK/cluster/_kmeans.py:1487-1490.                                   */
 int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* Xc, void* stream);
 /* The same, plus in the same pass what the later stages ask of the centred matrix: stats[0] = max |xc| (fp16 scales of the

@@ -38,6 +38,10 @@ class FakeKernels:
         x = _np(X).astype(np.float64)
         return torch.from_numpy(x.sum(0)), torch.from_numpy((x * x).sum(0))
 
+    def normalize_col_stats(self, X):
+        Xn = self.normalize_rows(X)
+        return (Xn,) + tuple(self.col_stats(Xn))
+
     def center_rows(self, X, mean32):
         return (X - mean32).contiguous()
 

@@ -584,3 +584,15 @@ def test_dedup_screen_flags_rows_it_cannot_decide(engine):
     X2 = plant_dupes(blobs(9000, 512, kc=4, seed=5), frac=20, seed=1)[0]
     engine.dedup(X2, float(thr), force='tc')
     assert K.dedup_stats['reswept_units'] == 0
+
+
+@pytest.mark.parametrize('N,d', [(5000, 512), (3001, 768), (1000, 1024), (77, 128), (300, 100)])
+def test_normalize_col_stats_fused(K, N, d):
+    """Encoder hand-off: normalise + column statistics in one pass = the two separate kernels (rows bit-equal)."""
+    X = blobs(N, d, kc=3, seed=N, normalize=False) * np.float32(2.5) + np.float32(0.3)
+    Xn, s, q = K.normalize_col_stats(dev(X))
+    want = K.normalize_rows(dev(X))
+    assert torch.equal(Xn, want)
+    ws, wq = K.col_stats(want)
+    np.testing.assert_allclose(s.cpu().numpy(), ws.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(q.cpu().numpy(), wq.cpu().numpy(), rtol=1e-12)

@@ -371,3 +371,18 @@ def test_tolerance_stopped_fits_also_need_no_extra_pass(eng):
         assert np.array_equal(r.labels.numpy(), lab)
         np.testing.assert_allclose(r.inertia, inertia, rtol=1e-5)
         np.testing.assert_allclose(sc[1:], rsc[1:], rtol=1e-5)
+
+
+def test_encoder_hand_off_normalises_in_the_first_pass(eng):
+    """SURVEY.md 8f item 2, second half: raw encoder outputs + normalize=True give what the reference gets from the
+    normalised embeddings FaceNet emits (encoders/facenet.py:153)."""
+    from oracle import restatement as RS
+    raw = blobs(1200, 512, kc=4, noise=1.0, seed=5, normalize=False) * np.float32(3.7)
+    Xn = RS.normalize_l2(raw).astype(np.float32)
+    ctx_a, a = eng.kmeans_sweep(raw, [2, 3, 4], 0, normalize=True)
+    ctx_b, b = eng.kmeans_sweep(Xn, [2, 3, 4], 0)
+    for ra, rb in zip(a, b):
+        assert torch.equal(ra.labels, rb.labels) and ra.n_iter == rb.n_iter
+        np.testing.assert_allclose(ra.inertia, rb.inertia, rtol=1e-6)
+    ref = RC.cluster_core(Xn, [2, 3, 4], 0)
+    assert all(np.array_equal(r.labels.numpy(), l) for r, l in zip(a, ref['labels']))

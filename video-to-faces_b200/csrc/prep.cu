@@ -76,6 +76,65 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
     }
 }
 
+// Encoder hand-off: FaceNet ends with F.normalize (encoders/facenet.py:153) and KMeans.fit starts with the
+// column statistics of what comes out (SK/cluster/_kmeans.py:292, 1487).  For embeddings that are still un-normalised on the
+// device both happen in ONE pass: warp per row (the row stays in registers between the norm and the divide), and every lane
+// keeps fp64 column sums / sums of squares of the normalised values for the 4*DV columns it owns; warps and CTAs are
+// combined in a fixed order (deterministic).  Saves the separate col_stats read of X.
+template <int DV>
+__global__ void __launch_bounds__(256) normalize_stats_kernel(const float* __restrict__ X, int64_t N, int d, float* __restrict__ Xn,
+                                                             double* __restrict__ part) {
+    extern __shared__ __align__(16) double sred[];     // [8 warps][2 * d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double cs[DV][4], cq[DV][4];
+#pragma unroll
+    for (int v = 0; v < DV; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cs[v][j] = 0.0; cq[v][j] = 0.0; }
+    int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (; row < N; row += stride) {
+        const float4* xr = reinterpret_cast<const float4*>(X + row * d);
+        float4 xv[DV];
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < DV; ++v) xv[v] = ldg_stream(xr + lane + 32 * v);
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+            s = fmaf(xv[v].x, xv[v].x, s); s = fmaf(xv[v].y, xv[v].y, s);
+            s = fmaf(xv[v].z, xv[v].z, s); s = fmaf(xv[v].w, xv[v].w, s);
+        }
+        s = warp_sum(s);
+        float nrm = sqrtf(s);
+        if (nrm < 10.f * 1.1920929e-07f) nrm = 1.f;               // same guard as vtf_normalize_rows
+        float4* outr = reinterpret_cast<float4*>(Xn + row * d);
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+            float4 a = xv[v];
+            a.x = __fdiv_rn(a.x, nrm); a.y = __fdiv_rn(a.y, nrm); a.z = __fdiv_rn(a.z, nrm); a.w = __fdiv_rn(a.w, nrm);
+            outr[lane + 32 * v] = a;
+            cs[v][0] += a.x; cs[v][1] += a.y; cs[v][2] += a.z; cs[v][3] += a.w;
+            cq[v][0] += (double)a.x * a.x; cq[v][1] += (double)a.y * a.y; cq[v][2] += (double)a.z * a.z; cq[v][3] += (double)a.w * a.w;
+        }
+    }
+    double* mine = sred + (size_t)warp * 2 * d;
+#pragma unroll
+    for (int v = 0; v < DV; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = 4 * (lane + 32 * v) + j;
+            mine[col] = cs[v][j];
+            mine[d + col] = cq[v][j];
+        }
+    __syncthreads();
+    double* out = part + (size_t)blockIdx.x * 2 * d;
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sred[(size_t)w * 2 * d + i];
+        out[i] = t;
+    }
+}
+
 template <bool NORMALIZE>
 static int launch_row_norm(const float* X, int64_t N, int d, float* Xn, float* sqn, void* stream, const char* what) {
     const int grid = (int)min((int64_t)num_sms() * 8, (N + 7) / 8);
@@ -264,6 +323,28 @@ int vtf_center_rows(const float* X, int64_t N, int d, const float* mean, float* 
     int grid = (int)min((int64_t)num_sms() * 16, (nvt + 255) / 256);
     VTF_LAUNCH(center_kernel, grid, 256, 0, stream, (const float4*)X, nvt, d / 4, (const float4*)mean, (float4*)Xc);
     VTF_CHECK_LAST("vtf_center_rows");
+    return VTF_OK;
+}
+
+size_t vtf_normalize_col_stats_ws_bytes(int d) { return (size_t)num_sms() * 2 * (size_t)d * sizeof(double); }
+
+int vtf_normalize_col_stats(const float* X, int64_t N, int d, float* Xn, double* col_sum, double* col_sumsq, void* ws, void* stream) {
+    VTF_REQUIRE(X && Xn && col_sum && col_sumsq && ws && N >= 0 && d > 0 && d % 128 == 0 && d <= 1024, "vtf_normalize_col_stats (d % 128 == 0, d <= 1024)");
+    const int grid = num_sms();
+    const size_t smem = (size_t)8 * 2 * d * sizeof(double);
+#define VTF_NS_CASE(DVv)                                                                                                       \
+    case DVv:                                                                                                                  \
+        VTF_CUDA(cudaFuncSetAttribute(normalize_stats_kernel<DVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),    \
+                 "vtf_normalize_col_stats/smem");                                                                              \
+        VTF_LAUNCH((normalize_stats_kernel<DVv>), grid, 256, smem, stream, X, N, d, Xn, (double*)ws);                          \
+        break;
+    switch (d / 128) {
+        VTF_NS_CASE(1) VTF_NS_CASE(2) VTF_NS_CASE(3) VTF_NS_CASE(4) VTF_NS_CASE(5) VTF_NS_CASE(6) VTF_NS_CASE(7) VTF_NS_CASE(8)
+    }
+#undef VTF_NS_CASE
+    VTF_CHECK_LAST("vtf_normalize_col_stats");
+    VTF_LAUNCH(reduce_parts_kernel, (2 * d + 255) / 256, 256, 0, stream, (const double*)ws, grid, 2 * d, col_sum, col_sumsq, d);
+    VTF_CHECK_LAST("vtf_normalize_col_stats/reduce");
     return VTF_OK;
 }
 

@@ -32,6 +32,8 @@ def build_parser():
     p.add_argument('--enc-oth-thr', metavar='FLOAT', type=float, default=0.9)
     p.add_argument('--group-log', action='store_true')
     p.add_argument('--features', metavar='NPY', help='precomputed embeddings [N,d] float32 (.npy), rows in sorted file order')
+    p.add_argument('--normalize-features', action='store_true',
+                   help='--features are raw encoder outputs: apply the L2 normalisation FaceNet ends with, fused into the first pass')
     p.add_argument('--ref-features', metavar='NPY', help='precomputed reference embeddings [R,d] (.npy), rows in sorted class order')
     # detection-stage flags of the reference CLI: parsed for compatibility, unused here
     for flag, kw in (('--save-frames', dict(action='store_true')), ('--save-rejects', dict(action='store_true')),

@@ -21,6 +21,8 @@ SIGNATURES = {
     'vtf_col_stats_ws_bytes': (c_sz, [c_int]),
     'vtf_col_stats': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     'vtf_center_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    'vtf_normalize_col_stats_ws_bytes': (c_sz, [c_int]),
+    'vtf_normalize_col_stats': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_center_rows_stats': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'vtf_build_cells_ws_bytes': (c_sz, [c_i64]),
     'vtf_build_cells': (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),

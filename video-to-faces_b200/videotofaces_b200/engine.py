@@ -284,21 +284,34 @@ class GroupingEngine:
         return bounds[self.comm.rank], bounds[self.comm.rank + 1]
 
     # ------------------------------------------------------------------------------ a6 prologue
-    def prepare(self, X):
+    def prepare(self, X, normalize=False):
+        """KMeans.fit's set-up (SK/cluster/_kmeans.py:1473-1496).  normalize=True: X are un-normalised encoder outputs and
+        the encoder's closing F.normalize (encoders/facenet.py:153) is applied here, fused with the column statistics."""
         X = self.upload_replicated(X)
         d_orig = X.shape[1]
         with self.span('prepare'):
-            ctx = self._prepare(self._pad16(X, 64 if X.shape[0] >= TC_MIN_ROWS and X.shape[1] <= 1024 else 16))
+            ctx = self._prepare(self._pad16(X, 64 if X.shape[0] >= TC_MIN_ROWS and X.shape[1] <= 1024 else 16), normalize)
         ctx.d_orig = d_orig
         ctx.tol /= d_orig                  # mean over the real columns: zero padding adds no variance
         return ctx
 
-    def _prepare(self, X):
+    def _prepare(self, X, normalize=False):
         ctx = FitContext()
-        ctx.X, ctx.N, ctx.d = X, X.shape[0], X.shape[1]
+        ctx.N, ctx.d = X.shape[0], X.shape[1]
         ctx.bounds = self._bounds(ctx.N)
         ctx.b, ctx.e = ctx.bounds[self.comm.rank], ctx.bounds[self.comm.rank + 1]
-        s, q = self.K.col_stats(X[ctx.b:ctx.e])
+        if normalize:
+            # one pass: Xn = x / |x| and the column sums of Xn for this rank's rows; the other ranks' rows are gathered
+            Xn_loc, s, q = self.K.normalize_col_stats(X[ctx.b:ctx.e])
+            if self.comm.active:
+                X = torch.empty_like(X)
+                X[ctx.b:ctx.e] = Xn_loc
+                self.comm.allgather_rows(X, ctx.bounds)
+            else:
+                X = Xn_loc
+        else:
+            s, q = self.K.col_stats(X[ctx.b:ctx.e])
+        ctx.X = X
         sq = torch.cat([s, q])
         self.comm.allreduce_sum(sq)
         s, q = sq[:ctx.d], sq[ctx.d:]
@@ -782,12 +795,12 @@ class GroupingEngine:
         C_new, C64, stats = K.lloyd_update(sums, counts, n_changed, C_old)
         return C_new, C64, stats.cpu().numpy()
 
-    def kmeans_sweep(self, X, clusters, rstate, inits=None, ctx=None):
+    def kmeans_sweep(self, X, clusters, rstate, inits=None, ctx=None, normalize=False):
         """grouping.py:99-101 for every k.  `inits[j]` (un-centred [k,d]) replaces k-means++ for k_j.
 
         Seeds are prefix-shared: every fit starts a fresh RandomState(rstate), so for equal
         n_local_trials the seed list of k is a prefix of that of k+1."""
-        ctx = ctx if ctx is not None else self.prepare(X)
+        ctx = ctx if ctx is not None else self.prepare(X, normalize)
         results = []
         seed_cache = {}
         if inits is None:

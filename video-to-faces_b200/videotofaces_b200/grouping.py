@@ -71,15 +71,16 @@ def classify_faces(paths, X, model, classif_params, R=None):
     sync()
 
 
-def cluster_labels(X, clusters, rstate, inits=None):
+def cluster_labels(X, clusters, rstate, inits=None, normalize=False):
     """The arithmetic of cluster_faces (grouping.py:95-120) without file system effects.
     Returns dict(clusters, labels [list of int32 arrays], scores [(k, sil, ch, db)], best_k,
-    inertia, n_iter, centers)."""
+    inertia, n_iter, centers).  normalize=True: X are un-normalised encoder outputs (a FaceNet without its closing
+    F.normalize, encoders/facenet.py:153); the normalisation is fused into the first pass over X."""
     eng = get_engine()
     n = X.shape[0]
     clusters = [c for c in clusters if c <= n]                                 # grouping.py:95
     with eng.solo_if(eng.too_small_to_shard(n)):
-        ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits)      # grouping.py:99-101
+        ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits, normalize=normalize)      # grouping.py:99-101
         scores = eng.cluster_scores(ctx, results)                              # grouping.py:104-108
     best_k = max(scores, key=lambda s: s[1])[0] if scores else None            # grouping.py:116 (first max)
     host = eng.to_host([r.labels for r in results] + [r.centers for r in results])      # one D2H sync for all labels and centres
@@ -89,12 +90,12 @@ def cluster_labels(X, clusters, rstate, inits=None):
                 centers=host[nk:], seeds=[r.seeds for r in results])
 
 
-def cluster_faces(paths, X, cluster_params):
-    """grouping.py:92-137."""
+def cluster_faces(paths, X, cluster_params, normalize=False):
+    """grouping.py:92-137.  `normalize` (not in the reference): see cluster_labels."""
     clusters, save_all, rstate, log, out_dir = cluster_params
     clusters = [c for c in clusters if c <= len(paths)]
     _say('Clustering images into %s groups' % ', '.join(str(cl) for cl in clusters))
-    res = cluster_labels(X, clusters, rstate)
+    res = cluster_labels(X, clusters, rstate, normalize=normalize)
     labels, scores = res['labels'], res['scores']
     if log and is_main():
         with open(osp.join(out_dir, 'faces', 'log_clustering.csv'), 'w') as f:

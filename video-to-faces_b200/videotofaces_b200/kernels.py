@@ -63,6 +63,20 @@ class CudaKernels:
         nv.call('vtf_center_rows', ptr(X), c_i64(N), c_int(d), ptr(mean32), ptr(out), stream())
         return out
 
+    def normalize_col_stats(self, X):
+        """(Xn, col_sum, col_sumsq): L2-normalised rows and their fp64 column statistics in one pass (d % 128 == 0, d <= 1024;
+        other widths: two passes)."""
+        N, d = self._chk(X)
+        if d % 128 != 0 or d > 1024:
+            Xn = self.normalize_rows(X)
+            return (Xn,) + tuple(self.col_stats(Xn))
+        out = torch.empty_like(X)
+        s = self.empty((d,), torch.float64)
+        q = self.empty((d,), torch.float64)
+        ws = self._workspace(nv.load().vtf_normalize_col_stats_ws_bytes(d))
+        nv.call('vtf_normalize_col_stats', ptr(X), c_i64(N), c_int(d), ptr(out), ptr(s), ptr(q), ptr(ws), stream())
+        return out, s, q
+
     def center_rows_stats(self, X, mean32):
         """(Xc, stats): stats = fp32 [max |xc|, max row |xc|^2], computed in the centring pass."""
         N, d = self._chk(X)

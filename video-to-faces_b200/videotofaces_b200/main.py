@@ -46,7 +46,7 @@ def video_to_faces(input_path=None, input_ext=None,
                    ref_dir=None, random_state=0, group_log=True,
                    enc_dup_thr=0.25, enc_oth_thr=0.9,
                    _test_enc=False, _test_exclude_other=False,
-                   features=None, ref_features=None):
+                   features=None, ref_features=None, normalize_features=False):
     if not validate_args(mode, input_path, out_dir, style, group_mode, video_reader, det_model, enc_model):
         return
     if mode != 'grouping':
@@ -93,7 +93,9 @@ def video_to_faces(input_path=None, input_ext=None,
     if enc_dup_thr and enc_dup_thr != -1:                                      # main.py:72-74
         feats, imgpaths = remove_dupes_overall(feats, imgpaths, ('enc', enc_dup_thr, save_dupes, out_dir))
     if group_mode == 'clustering':                                             # main.py:75-77
-        cluster_faces(imgpaths, feats, (clusters, clusters_save_all, random_state, group_log, out_dir))
+        # normalize_features: `features` are raw encoder outputs (FaceNet without its closing F.normalize, facenet.py:153);
+        # the normalisation is fused into the first pass of the clustering (dedup / classify normalise on their own)
+        cluster_faces(imgpaths, feats, (clusters, clusters_save_all, random_state, group_log, out_dir), normalize=normalize_features)
     if group_mode == 'classification':                                         # main.py:78-80
         R = _load_features(ref_features) if ref_features is not None else None
         classify_faces(imgpaths, feats, encoder, (refs, enc_oth_thr, group_log, out_dir), R=R)
