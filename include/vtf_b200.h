@@ -270,8 +270,13 @@ int vtf_dedup_refine(const float* Xn, int64_t N, int d, int rank, int world, uin
  * argmin, and flags unit_flag[i / 256] (*n_flagged += newly flagged units) for rows whose decision at `thr` the screen
  * cannot guarantee: exact minimum above thr although an unseen column might be below (1 - g_unseen/scale^2 - eps <= thr;
  * eps = bound of the screen's error, 1e-3 for unit rows; thr = NaN: never).  The flagged units are re-swept with the split
- * operands by vtf_cosine_dedup_tc_units (unit_list: device array of unit indices) followed by vtf_dedup_refine.     */
-int vtf_dedup_screen(const void* Hi, int64_t N, int64_t P, int d, int rank, int world, void* cand, void* stream);
+ * operands by vtf_cosine_dedup_tc_units (unit_list: device array of unit indices) followed by vtf_dedup_refine.
+ * The screen cuts the triangle into column chunks of <= 48 MB of operand (one launch each, so a chunk comes from DRAM once)
+ * and claims the (unit x chunk) items of a launch from work_counters[launch], longest first: the caller passes
+ * vtf_dedup_screen_launches(N, d) ZEROED counters.                                                                      */
+int vtf_dedup_screen_launches(int64_t N, int d);
+int vtf_dedup_screen(const void* Hi, int64_t N, int64_t P, int d, int rank, int world, void* cand, uint32_t* work_counters,
+                     int n_counters, void* stream);
 int vtf_dedup_refine4(const float* Xn, int64_t N, int d, int rank, int world, const void* cand, float scale, float thr,
                       float eps, uint64_t* key, int32_t* unit_flag, uint32_t* n_flagged, void* stream);
 int vtf_cosine_dedup_tc_units(const void* Hi, const void* Lo, int64_t N, int64_t P, int d, float scale,

@@ -399,7 +399,11 @@ class CudaKernels:
             return key
         cand = self.empty((N, 8, 2), torch.int32)
         flags = self.zeros((P // 256 + 1,), torch.int32)         # [units] flags + [1] count
-        nv.call('vtf_dedup_screen', ptr(hi), c_i64(N), c_i64(P), c_int(d), c_int(rank), c_int(world), ptr(cand), stream())
+        n_launch = int(nv.load().vtf_dedup_screen_launches(N, d))
+        counters = self.zeros((max(n_launch, 1),), torch.int32)   # one claim counter per column chunk
+        nv.call('vtf_dedup_screen', ptr(hi), c_i64(N), c_i64(P), c_int(d), c_int(rank), c_int(world), ptr(cand), ptr(counters),
+                c_int(n_launch), stream())
+        self.dedup_stats['screen_launches'] = n_launch
         nv.call('vtf_dedup_refine4', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(cand), c_f32(scale),
                 c_f32(float('nan') if thr is None else float(thr)), c_f32(self.DEDUP_SCREEN_EPS), ptr(key), ptr(flags),
                 nv.c_vp(flags.data_ptr() + 4 * (P // 256)), stream())
