@@ -627,7 +627,9 @@ def run_config(cfg, args, env, steps, warmup, headline):
         def api():
             if kind == 'cluster':
                 return cluster_labels(Xh, cfg['ks'], 0)
-            r = dedup_rows(Xh, cfg['dup_thr'])
+            # the drop-in's own flow (videotofaces_b200/main.py, reference main.py:72-80): the surviving rows are only handed to
+            # the grouping call, so they stay in HBM; the dup set, distances, labels and [N,R] distances come back to the host
+            r = dedup_rows(Xh, cfg['dup_thr'], keep_on_device=True)
             if kind == 'dedup_classify':
                 r['lab'] = classify(r['kept'], data['R'], ['c%02d' % i for i in range(cfg['n_refs'])], cfg['oth_thr'], False, None, None)[0]
             return r
@@ -646,9 +648,10 @@ def run_config(cfg, args, env, steps, warmup, headline):
             what = 'videotofaces_b200.grouping.cluster_labels(X_host, %s, 0)' % ('[2..%d]' % cfg['ks'][-1])
             h2d = int(Xh.nbytes)
         else:
-            d2h = int(res_api['kept'].nbytes + 16 * N + 8 * res_api['idx'].size + res_api['lab'].nbytes + res_api['lab'].size * 4 * cfg['n_refs'])
-            h2d = int(Xh.nbytes + res_api['kept'].nbytes + data['R'].nbytes)
-            what = 'videotofaces_b200.dupes.dedup_rows(X_host, 0.2) -> grouping.classify(kept_host, R_host, classes, 0.9, ...)'
+            d2h = int(8 * N + res_api['lab'].nbytes + res_api['lab'].size * 4 * cfg['n_refs'])      # packed keys, labels, [N,R] distances
+            h2d = int(Xh.nbytes + data['R'].nbytes + 8 * (N - res_api['idx'].size))                  # X, refs, kept-row indices
+            what = ('videotofaces_b200.dupes.dedup_rows(X_host, 0.2, keep_on_device=True) -> grouping.classify(kept, R_host, classes, '
+                    '0.9, ...): the flow of video_to_faces(mode="grouping") after the encoder')
         rec['e2e'] = dict(value=N / float(t_e2e.item()), unit='embeddings/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                           ms_per_step=float(t_e2e.item()) * 1e3, api=what)
     else:

@@ -67,3 +67,19 @@ def test_done_is_printed_like_the_reference(cpu_engine, tmp_path, capsys):
     DC.fake_faces(str(tmp_path), 40)
     video_to_faces(mode='grouping', style='live', out_dir=str(tmp_path), clusters='2-3', enc_dup_thr=-1, features=X)
     assert capsys.readouterr().out.endswith('\nDone\n')
+
+
+def test_keep_on_device_hands_the_survivors_over_as_a_tensor(cpu_engine, tmp_path):
+    """video_to_faces keeps the rows that survive dedup on the device for the grouping call (main.py:74-80 only passes them
+    on); the public entry point returns numpy unless asked."""
+    import torch
+    X = blobs(300, 512, kc=3, noise=0.5, seed=1)
+    X[200:220] = X[10:30]                                              # exact duplicates
+    a = vdupes.dedup_rows(X, 0.2)
+    b = vdupes.dedup_rows(X, 0.2, keep_on_device=True)
+    assert isinstance(a['kept'], np.ndarray) and isinstance(b['kept'], torch.Tensor)
+    assert np.array_equal(a['kept'], b['kept'].cpu().numpy()) and np.array_equal(a['idx'], b['idx'])
+    assert a['idx'].size >= 20
+    paths = DC.fake_faces(str(tmp_path), X.shape[0])
+    Xk, goods = vdupes.remove_dupes_overall(X, paths, ('enc', 0.2, False, str(tmp_path)), keep_on_device=True)
+    assert isinstance(Xk, torch.Tensor) and Xk.shape[0] == len(goods) == X.shape[0] - a['idx'].size

@@ -119,6 +119,9 @@ def test_device_resident_embeddings_go_through_the_drop_in_entry_points(tmp_path
                                              ('enc', 0.2, True, str(tmp_path / 'dev')))
     assert isinstance(Xd, torch.Tensor) and Xd.is_cuda                     # no host copy of the survivors
     assert np.array_equal(Xd.cpu().numpy(), Xh)
+    # a HOST matrix with keep_on_device (what video_to_faces does): one upload, the survivors stay in HBM
+    r = dupes.dedup_rows(X, 0.2, keep_on_device=True)
+    assert isinstance(r['kept'], torch.Tensor) and r['kept'].is_cuda and np.array_equal(r['kept'].cpu().numpy(), Xh)
     assert [osp.basename(g) for g in goods_d] == [osp.basename(g) for g in goods_h]
     assert sorted(os.listdir(tmp_path / 'dev' / 'intermediate' / 'dupes3')) == sorted(os.listdir(tmp_path / 'host' / 'intermediate' / 'dupes3'))
     a = grouping.cluster_labels(Xh, [2, 3, 4], 0)

@@ -491,6 +491,116 @@ __global__ void __launch_bounds__(256) kpp_chunk_int_kernel(const float* __restr
     }
 }
 
+// The same distances on the fp64 TENSOR pipe.  The CUDA cores of B200 retire DFMA at about 1/8 of the fp32 rate, which made
+// the kernel above fp64-bound (0.45 of HBM at T = 3); mma.sync.m8n8k4.f64 computes an 8 x 8 x 4 block of exact products with
+// fp64 accumulation per instruction, and the candidates (T <= 8) fill its N dimension.  Warp = 16 rows per pass (two 8-row
+// groups that share every candidate read); lane (r = lane / 4, q = lane % 4) loads the float4 at columns 16 j + 4 q of row r
+// and feeds element m of it to MMA m of the step, the B operand taking the matching candidate elements from shared memory
+// (fp64, rows padded by 16 B so that the eight candidates start in different banks).  Products of two fp32 values are exact in
+// fp64, so only the ORDER of the fp64 additions differs from the kernel above (and from any BLAS): after the rounding to fp32
+// the distances are equal except where the fp64 sums straddle a rounding boundary (test_kpp_dist_matches_upcast_path).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2) kpp_dist_mma_kernel(const float* __restrict__ X, int64_t N, int d, const float* __restrict__ cand,
+                                                           int T, const float* __restrict__ closest, const double* __restrict__ xsq,
+                                                           float* __restrict__ out, double* __restrict__ part) {
+    extern __shared__ __align__(16) double sc[];   // [T][d + 2] candidates in fp64
+    __shared__ double s_cc[kMaxTrials];
+    __shared__ double s_pot[8][kMaxTrials];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ld = d + 2;
+    for (int i = threadIdx.x; i < T * d; i += blockDim.x) sc[(i / d) * ld + (i % d)] = (double)__ldg(cand + i);
+    __syncthreads();
+    if (warp < T) {
+        double s = 0.0;
+        for (int j = lane; j < d; j += 32) { const double c = sc[warp * ld + j]; s = fma(c, c, s); }
+        s = warp_sum(s);
+        if (lane == 0) s_cc[warp] = s;
+    }
+    __syncthreads();
+
+    const int r = lane >> 2, q = lane & 3;
+    const bool bcol = r < T;                                   // this lane's B column is a real candidate
+    const double* bsrc = sc + (size_t)(bcol ? r : 0) * ld + 4 * q;
+    const int t0 = 2 * q, t1 = 2 * q + 1;                      // the candidates whose results land in this lane
+    double pot0 = 0.0, pot1 = 0.0;
+    const int nchunk = d >> 4;                                 // 16 columns per step
+
+    int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 16;
+    const int64_t stride = (int64_t)gridDim.x * 8 * 16;
+    for (; row0 < N; row0 += stride) {
+        const int64_t ra = row0 + r, rb = row0 + 8 + r;
+        const float4* xa = reinterpret_cast<const float4*>(X + (ra < N ? ra : row0) * d) + q;
+        const float4* xb = reinterpret_cast<const float4*>(X + (rb < N ? rb : row0) * d) + q;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        int j = 0;
+        for (; j + 4 <= nchunk; j += 4) {
+            float4 fa[4], fb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { fa[u] = ldg_stream(xa + 4 * (j + u)); fb[u] = ldg_stream(xb + 4 * (j + u)); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double2 c01 = make_double2(0.0, 0.0), c23 = c01;
+                if (bcol) {
+                    c01 = *reinterpret_cast<const double2*>(bsrc + 16 * (j + u));
+                    c23 = *reinterpret_cast<const double2*>(bsrc + 16 * (j + u) + 2);
+                }
+                dmma884(a0, a1, (double)fa[u].x, c01.x); dmma884(b0, b1, (double)fb[u].x, c01.x);
+                dmma884(a0, a1, (double)fa[u].y, c01.y); dmma884(b0, b1, (double)fb[u].y, c01.y);
+                dmma884(a0, a1, (double)fa[u].z, c23.x); dmma884(b0, b1, (double)fb[u].z, c23.x);
+                dmma884(a0, a1, (double)fa[u].w, c23.y); dmma884(b0, b1, (double)fb[u].w, c23.y);
+            }
+        }
+        for (; j < nchunk; ++j) {
+            const float4 fa = ldg_stream(xa + 4 * j), fb = ldg_stream(xb + 4 * j);
+            double2 c01 = make_double2(0.0, 0.0), c23 = c01;
+            if (bcol) {
+                c01 = *reinterpret_cast<const double2*>(bsrc + 16 * j);
+                c23 = *reinterpret_cast<const double2*>(bsrc + 16 * j + 2);
+            }
+            dmma884(a0, a1, (double)fa.x, c01.x); dmma884(b0, b1, (double)fb.x, c01.x);
+            dmma884(a0, a1, (double)fa.y, c01.y); dmma884(b0, b1, (double)fb.y, c01.y);
+            dmma884(a0, a1, (double)fa.z, c23.x); dmma884(b0, b1, (double)fb.z, c23.x);
+            dmma884(a0, a1, (double)fa.w, c23.y); dmma884(b0, b1, (double)fb.w, c23.y);
+        }
+        // lane holds x_row . c_t for t = 2q, 2q + 1 (rows ra and rb)
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int64_t row = g ? rb : ra;
+            if (row < N && t0 < T) {
+                const double xs = __ldg(xsq + row);
+                const float prev = closest ? __ldg(closest + row) : INFINITY;
+                // ((-2 x.c) + |c|^2) + |x|^2 in fp64, then fp32, then clamp (pairwise.py:632-636, 413)
+                float dist = (float)((-2.0 * (g ? b0 : a0) + s_cc[t0]) + xs);
+                dist = fminf(fmaxf(dist, 0.f), prev);
+                out[(size_t)t0 * N + row] = dist;
+                pot0 += (double)dist;
+                if (t1 < T) {
+                    float dist1 = (float)((-2.0 * (g ? b1 : a1) + s_cc[t1]) + xs);
+                    dist1 = fminf(fmaxf(dist1, 0.f), prev);
+                    out[(size_t)t1 * N + row] = dist1;
+                    pot1 += (double)dist1;
+                }
+            }
+        }
+    }
+    // lanes with the same q hold partial potentials of the same two candidates
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        pot0 += __shfl_xor_sync(0xffffffffu, pot0, o);
+        pot1 += __shfl_xor_sync(0xffffffffu, pot1, o);
+    }
+    if (lane < 4) { s_pot[warp][2 * lane] = pot0; s_pot[warp][2 * lane + 1] = pot1; }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += s_pot[w][threadIdx.x];
+        part[(size_t)blockIdx.x * T + threadIdx.x] = s;
+    }
+}
+
 static int kpp_grid() { return num_sms() * 4; }
 
 }  // namespace vtf
@@ -559,7 +669,13 @@ int vtf_kpp_dist(const float* Xc, int64_t N, int d, const float* cand, int T, co
                  "vtf_kpp_dist");                                                                                             \
         VTF_LAUNCH((kpp_dist_kernel<TTv, Rv, Hv>), grid, 256, smem, stream, Xc, N, d, cand, T, closest, xsq, out, (double*)ws); \
     } while (0)
-    if (T <= 4) { if (xsq) VTF_KPP_LAUNCH(4, 4, true); else VTF_KPP_LAUNCH(4, 4, false); }
+    static int use_mma = -1;
+    if (use_mma < 0) { const char* e = getenv("VTF_KPP_MMA"); use_mma = e ? atoi(e) : 1; }
+    const size_t smem_mma = (size_t)T * (d + 2) * sizeof(double);
+    if (use_mma && xsq && d % 16 == 0 && smem_mma <= 100 * 1024) {
+        VTF_CUDA(cudaFuncSetAttribute(kpp_dist_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "vtf_kpp_dist");
+        VTF_LAUNCH(kpp_dist_mma_kernel, grid, 256, smem_mma, stream, Xc, N, d, cand, T, closest, xsq, out, (double*)ws);
+    } else if (T <= 4) { if (xsq) VTF_KPP_LAUNCH(4, 4, true); else VTF_KPP_LAUNCH(4, 4, false); }
     else { if (xsq) VTF_KPP_LAUNCH(kMaxTrials, 2, true); else VTF_KPP_LAUNCH(kMaxTrials, 2, false); }
 #undef VTF_KPP_LAUNCH
     VTF_CHECK_LAST("vtf_kpp_dist");

@@ -25,13 +25,17 @@ def _write_dupes_log(path, filenames, mins, inds, is_dup, measure_name):
             f.write('%s,%s,%s,%s\n' % (filenames[i], filenames[inds[i]], str(mins[i]), '1' if is_dup[i] else '0'))
 
 
-def dedup_rows(X, threshold):
+def dedup_rows(X, threshold, keep_on_device=False):
     """The arithmetic of remove_dupes_overall's 'enc' branch (dupes.py:60-68) without file system effects: returns
-    dict(kept [N - n_dup, d] (numpy for a host X, a CUDA tensor for a device X), idx int64 [n_dup], mins fp32 [N],
-    inds int64 [N])."""
+    dict(kept [N - n_dup, d] (numpy for a host X, a CUDA tensor for a device X or with keep_on_device), idx int64 [n_dup],
+    mins fp32 [N], inds int64 [N]).  keep_on_device: the surviving rows stay in HBM for the grouping call that follows
+    (main.py:74-80 only passes them on) -- one upload of X instead of upload + download + upload."""
     eng = get_engine()
-    mins, inds, idx = eng.dedup(X, threshold)                                  # dupes.py:60-65
     on_device = hasattr(X, 'is_cuda') and X.is_cuda                            # encoder output still on the GPU (section 8f item 2)
+    if keep_on_device and not on_device:
+        X = eng.to_device(X)                                                   # the ONE host-to-device copy of the flow
+        on_device = True
+    mins, inds, idx = eng.dedup(X, threshold)                                  # dupes.py:60-65
     if on_device:
         kept = eng.delete_rows(X, idx) if idx.size else X.clone()              # stays in HBM for the grouping that follows
     else:
@@ -39,8 +43,9 @@ def dedup_rows(X, threshold):
     return dict(kept=kept, idx=idx, mins=mins, inds=inds)
 
 
-def remove_dupes_overall(X, filenames, dup_params):
-    """Returns (X_kept float32 [N - n_dup, d], goods) exactly like dupes.py:51-92."""
+def remove_dupes_overall(X, filenames, dup_params, keep_on_device=False):
+    """Returns (X_kept float32 [N - n_dup, d], goods) exactly like dupes.py:51-92.  keep_on_device (used by video_to_faces,
+    which only hands X_kept to the grouping call): X_kept is a CUDA tensor instead of a numpy array ('enc' branch)."""
     measure_type, threshold, save_dupes, out_dir = dup_params
     eng = get_engine()
     n = X.shape[0]
@@ -48,7 +53,7 @@ def remove_dupes_overall(X, filenames, dup_params):
     if is_hash:
         mins, inds, idx = eng.dedup_hash(X, threshold)                         # dupes.py:55-58, 62-65
     else:
-        r = dedup_rows(X, threshold)                                           # dupes.py:60-65, 68
+        r = dedup_rows(X, threshold, keep_on_device)                           # dupes.py:60-65, 68
         mins, inds, idx = r['mins'], r['inds'], r['idx']
     is_dup = np.zeros(n, dtype=bool)
     is_dup[idx] = True

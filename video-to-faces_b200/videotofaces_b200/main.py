@@ -91,7 +91,8 @@ def video_to_faces(input_path=None, input_ext=None,
             return
 
     if enc_dup_thr and enc_dup_thr != -1:                                      # main.py:72-74
-        feats, imgpaths = remove_dupes_overall(feats, imgpaths, ('enc', enc_dup_thr, save_dupes, out_dir))
+        # the surviving rows stay on the device: the grouping call below is their only consumer
+        feats, imgpaths = remove_dupes_overall(feats, imgpaths, ('enc', enc_dup_thr, save_dupes, out_dir), keep_on_device=True)
     if group_mode == 'clustering':                                             # main.py:75-77
         # normalize_features: `features` are raw encoder outputs (FaceNet without its closing F.normalize, facenet.py:153);
         # the normalisation is fused into the first pass of the clustering (dedup / classify normalise on their own)
