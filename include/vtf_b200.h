@@ -344,6 +344,9 @@ int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, float scale
 int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int d, float scale,
                       const int32_t* chunk_cell, int n_cells, int rank, int world, float* cellsum,
                       uint32_t* work_counter, uint64_t* tiles_done, void* stream);
+/* Debugging aid: with VTF_SWEEP_TIMING=1 in the environment vtf_sil_sweep_sym records the %globaltimer value of its first CTA
+ * entry and last CTA exit; this returns the pair of the last launch (ns) after synchronising the device.            */
+int vtf_debug_sweep_timing(uint64_t* out2);
 /* finish: for labelling l (k_l clusters), per real row: a = S_own/(n_own-1),
  * b = min_{c != own} S_c/n_c, s = (b-a)/max(a,b) (0 for singleton clusters, :323), and
  * out[l] += sum_i s_i in fp64.  From the exact path: vtf_sil_finish_rows on rowsum[N,k].    */

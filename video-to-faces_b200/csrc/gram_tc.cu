@@ -73,7 +73,15 @@ struct Params {
     // the squared norms AS THE TENSOR CORE COMPUTES THEM (same instruction shape, same accumulation order as in the sweep).
     float* diag_out;
     float diag_scale;
+    // debugging aid (VTF_SWEEP_TIMING=1): [0] = min over CTAs of %globaltimer at entry, [1] = max at exit
+    unsigned long long* timing;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Work list shared by the three warp roles (they must walk it identically).  `w` = index of the work item.
 //   full sweep: item -> (row unit, column segment);  rbu = row unit (CPC row blocks), tiles [t0, t1)
@@ -171,6 +179,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (prm.timing && threadIdx.x == 0) atomicMin(prm.timing, globaltimer_ns());
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -513,6 +522,7 @@ sil_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     tc_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's shared memory until the end
+    if (prm.timing && threadIdx.x == 0) atomicMax(prm.timing + 1, globaltimer_ns());
     if (warp == 1) {
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -605,7 +615,7 @@ extern "C" int vtf_sil_sweep(const void* Xh, const void* aug, int64_t P, int d, 
     prm.flush_scale = 1.41421356237f / scale;
     prm.sym_rank = 0; prm.sym_world = 1;
     prm.work_counter = nullptr; prm.n_items = 0; prm.tiles_done = nullptr; prm.chunk_tiles = 0;
-    prm.diag_out = nullptr; prm.diag_scale = 0.f;
+    prm.diag_out = nullptr; prm.diag_scale = 0.f; prm.timing = nullptr;
     const int64_t n_units = units * prm.n_seg;
     if (pair) {
         const int grid = 2 * (int)min(slots, n_units);
@@ -645,11 +655,29 @@ extern "C" int vtf_sil_diag(const void* Xh, const void* aug, int64_t P, int d, f
     prm.flush_scale = 0.f;
     prm.sym_rank = 0; prm.sym_world = 1;
     prm.work_counter = nullptr; prm.n_items = 0; prm.tiles_done = nullptr; prm.chunk_tiles = 0;
-    prm.diag_out = out; prm.diag_scale = out_scale;
+    prm.diag_out = out; prm.diag_scale = out_scale; prm.timing = nullptr;
     const int64_t units = prm.n_rb / 2;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), units);
     if (d <= 512) return tc::launch<true, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
     return tc::launch<false, 6, true, false>(ma, mb, maa, mab, prm, grid, stream);
+}
+
+// VTF_SWEEP_TIMING=1: the symmetric sweep records its own first-entry / last-exit %globaltimer values (a cross-check of the
+// event-based timings); vtf_debug_sweep_timing returns the last launch's pair.
+static unsigned long long* g_sweep_timing = nullptr;
+static unsigned long long* sweep_timing_buffer(void* stream) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("VTF_SWEEP_TIMING"); on = (e && atoi(e)) ? 1 : 0; }
+    if (!on) return nullptr;
+    if (!g_sweep_timing && cudaMalloc(&g_sweep_timing, 16) != cudaSuccess) { g_sweep_timing = nullptr; return nullptr; }
+    const unsigned long long init[2] = {~0ull, 0ull};
+    cudaMemcpyAsync(g_sweep_timing, init, 16, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return g_sweep_timing;
+}
+
+extern "C" int vtf_debug_sweep_timing(uint64_t* out2) {
+    if (!g_sweep_timing || !out2) return VTF_ERR_ARG;
+    return cudaMemcpy(out2, g_sweep_timing, 16, cudaMemcpyDeviceToHost) == cudaSuccess ? VTF_OK : VTF_ERR_CUDA;
 }
 
 // Symmetric form: D_pq = D_qp, so only tiles on or above the diagonal are computed (half the MMAs, half the L2
@@ -683,6 +711,7 @@ extern "C" int vtf_sil_sweep_sym(const void* Xh, const void* aug, int64_t P, int
     prm.sym_rank = rank; prm.sym_world = world;
     prm.work_counter = work_counter; prm.n_items = 0; prm.tiles_done = (unsigned long long*)tiles_done;
     prm.diag_out = nullptr; prm.diag_scale = 0.f;
+    prm.timing = sweep_timing_buffer(stream);
     const int64_t U = prm.n_rb / 2;
     // column chunk: <= 32 MB of B operand (a quarter of the 126 MB L2, so the chunk being left and the one being
     // entered both stay resident), 16..256 tiles; VTF_SWEEP_CHUNK overrides.  Same-box A/B at 1M x 512 (static /

@@ -990,30 +990,33 @@ class GroupingEngine:
         K, comm = self.K, self.comm
         if not self.dynamic or not getattr(K, 'dynamic_schedule', False):
             return None
+        if not comm.active:
+            # one process, or a rank running un-sharded (solo_if): a private counter -- the ranks' shared one would hand
+            # this rank's items to the others, which are not part of this sweep
+            if getattr(self, '_wc_local', None) is None:
+                self._wc_local = K.zeros((16,), torch.int32)
+            K.shared_zero(self._wc_local.data_ptr(), 4)        # stream order: after the previous sweep, before this one
+            return self._wc_local.data_ptr()
         if self._wc is None:
             try:
-                if comm.active:
-                    ok, addr = 1, 0
-                    box = [None]
-                    if comm.rank == 0:
-                        try:
-                            addr, box[0] = K.shared_alloc(64)
-                        except Exception:  # noqa: BLE001
-                            box[0] = None
-                    comm.broadcast_object(box, src=0)
-                    if box[0] is None:
+                ok, addr = 1, 0
+                box = [None]
+                if comm.rank == 0:
+                    try:
+                        addr, box[0] = K.shared_alloc(64)
+                    except Exception:  # noqa: BLE001
+                        box[0] = None
+                comm.broadcast_object(box, src=0)
+                if box[0] is None:
+                    ok = 0
+                elif comm.rank != 0:
+                    try:
+                        addr = K.shared_open(box[0])
+                    except Exception:  # noqa: BLE001
                         ok = 0
-                    elif comm.rank != 0:
-                        try:
-                            addr = K.shared_open(box[0])
-                        except Exception:  # noqa: BLE001
-                            ok = 0
-                    flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
-                    comm.allreduce_min(flag)                       # all ranks or none
-                    self._wc = (addr, None) if int(flag.item()) == 1 else False
-                else:
-                    t = K.zeros((16,), torch.int32)
-                    self._wc = (t.data_ptr(), t)
+                flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                comm.allreduce_min(flag)                       # all ranks or none
+                self._wc = (addr, None) if int(flag.item()) == 1 else False
             except Exception:  # noqa: BLE001
                 self._wc = False
         if self._wc is False:
