@@ -380,7 +380,7 @@ def phase_table(cfg, N, d, phases_ms, pk, world, info):
 def committed_traffic(cfg, N, d, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel -- NOT measured in this run: read from the
     committed `ncu --set full` capture of the same shape, when there is one."""
-    name = {'cluster': 'sweep', 'dedup_cluster': 'sweep', 'dedup_classify': 'dedup_screen'}[cfg['kind']]
+    name = {'cluster': 'sweep', 'dedup_cluster': 'sweep', 'dedup_classify': 'dedup_screen_v2'}[cfg['kind']]
     for rnd in ('r02', 'r01'):
         try:
             with open(osp.join(ROOT, 'profiles', '%s_%s_ncu_summary.json' % (rnd, name))) as f:
@@ -558,7 +558,7 @@ def run_config(cfg, args, env, steps, warmup, headline):
         executed = fl if dom == 'sil_sweep' else fl * (3.0 if dstats.get('mode') == 'split' else
                                                        1.0 + 3.0 * dstats.get('reswept_units', 0) / max(dstats.get('units', 1), 1))
         rec['roofline'] = dict(
-            bound='tensor', kernel=('sil_sweep_kernel' if dom == 'sil_sweep' else 'dedup_sweep_kernel') +
+            bound='tensor', kernel=('sil_sweep_kernel' if dom == 'sil_sweep' else 'dedup_screen_kernel') +
             ' (tcgen05 cta_group::2 kind::f16, fp32 accumulate in TMEM)' + ('' if dom == 'sil_sweep' else ' [%s]' % dstats),
             achieved=executed / (t_ms * 1e-3) / 1e12, peak=peak, unit='TFLOP/s', frac=executed / (t_ms * 1e-3) / 1e12 / peak,
             achieved_algorithmic=alg / (t_ms * 1e-3) / 1e12, frac_algorithmic=alg / (t_ms * 1e-3) / 1e12 / peak,

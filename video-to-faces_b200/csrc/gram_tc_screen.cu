@@ -49,6 +49,9 @@ struct ScreenParams {
     unsigned int* work_counter;   // zero at launch; claimed with atomicAdd
 };
 
+#ifndef VTF_SCREEN_RELAXED
+#define VTF_SCREEN_RELAXED 1   // accumulator-drained arrive without .release.cluster (a membar per arrive; tc_common.cuh): TMEM reads are ordered by tcgen05.wait::ld + fence
+#endif
 constexpr int kSStages = 6;
 constexpr int kSBlock = BM * BK * 2;            // 16 KB: 128 rows of one k-block
 
@@ -275,7 +278,7 @@ dedup_screen_kernel(const __grid_constant__ CUtensorMap map_hi, const ScreenPara
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote<false>(tempty_bar(as), 0u);
+                if (lane == 0) mbar_arrive_remote<VTF_SCREEN_RELAXED != 0>(tempty_bar(as), 0u);
                 if (++as == 2) { as = 0; acc_ph ^= 1u; }
             }
             if (i < prm.N) {
