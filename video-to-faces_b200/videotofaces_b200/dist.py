@@ -89,6 +89,15 @@ class Comm:
                 self._dist.broadcast(parts[r], src=self._global(r), group=self.group)
         return full
 
+    def allgather_pieces(self, full, bounds, lo, hi):
+        """Equal shards only: every rank filled rows bounds[rank] + [lo, hi) of `full`; afterwards every rank holds those rows
+        of every shard (one piece of a pipelined allgather_rows; the pieces of the ranks are not adjacent, hence the list)."""
+        if not self.active:
+            return full
+        outs = [full[bounds[r] + lo:bounds[r] + hi] for r in range(self.world)]
+        self._dist.all_gather(outs, outs[self.rank], group=self.group)
+        return full
+
     def _global(self, r):
         return r if self.group is None else self._dist.get_global_rank(self.group, r)
 

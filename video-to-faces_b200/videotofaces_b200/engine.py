@@ -165,6 +165,35 @@ class GroupingEngine:
         bounds = self._bounds(n)
         b, e = bounds[self.comm.rank], bounds[self.comm.rank + 1]
         full = torch.empty(A.shape, dtype=torch.float32, device=self.device)
+        sizes = {bounds[r + 1] - bounds[r] for r in range(self.comm.world)}
+        chunks = int(os.environ.get('VTF_UPLOAD_CHUNKS', '4'))
+        if (self.device.type == 'cuda' and len(sizes) == 1 and chunks > 1 and A.is_pinned() and
+                (e - b) * A.shape[1] * 4 >= (32 << 20) * chunks):
+            # Pipelined: the shard crosses PCIe in `chunks` pieces on a copy stream while the pieces that have arrived are
+            # already being exchanged over NVLink (piece c of every rank; the pieces of one exchange are not adjacent in
+            # `full`, so the collective takes a list of views).  Hides the all-gather behind the host-to-device copy.
+            m = (e - b + chunks - 1) // chunks
+            main = torch.cuda.current_stream()
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            cs.wait_stream(main)                                   # `full` was allocated on the main stream
+            full.record_stream(cs)
+            evs = []
+            with torch.cuda.stream(cs):
+                for c in range(chunks):
+                    lo, hi = b + c * m, min(e, b + (c + 1) * m)
+                    if hi > lo:
+                        full[lo:hi].copy_(A[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    evs.append(ev)
+            for c in range(chunks):
+                main.wait_event(evs[c])
+                lo_c, hi_c = c * m, min(e - b, (c + 1) * m)
+                if hi_c > lo_c:
+                    self.comm.allgather_pieces(full, bounds, lo_c, hi_c)
+            return full
         full[b:e].copy_(A[b:e], non_blocking=True)
         self.comm.allgather_rows(full, bounds)
         return full
