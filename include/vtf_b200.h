@@ -376,6 +376,11 @@ int vtf_shared_zero(void* ptr, size_t bytes, void* stream);
 int vtf_shared_close(void* ptr);
 int vtf_shared_free(void* ptr);
 
+/* Host matrix in PAGEABLE memory -> device (main.py:71 hands the grouping stage an ordinary numpy array): n_threads native
+ * threads copy 8 MB pieces into page-locked double buffers and queue each piece's DMA on their own streams, so the host copies
+ * run in parallel and overlap the transfers; `stream` waits for all pieces (nothing is ordered before that).  Returns after the
+ * host side is done: the source may be reused at once.  Pinned sources: use one plain cudaMemcpyAsync instead.            */
+int vtf_upload_pageable(const void* src_host, void* dst_dev, size_t bytes, int n_threads, void* stream);
 /* ---- f4: output stage (grouping.py:78-84, 122-137; dupes.py:70-79) -- HOST code, no kernel -----------------------
  * A batch of independent file operations on native threads: op 0 = copy src -> dst (shutil.copyfile: contents only,
  * copy_file_range with a read/write fallback), 1 = move (os.replace), 2 = remove (os.remove; dst ignored).  Paths are

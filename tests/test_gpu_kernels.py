@@ -555,6 +555,28 @@ def test_dedup_screen_equals_split_sweep(engine, N, d):
     assert (i_scr == rinds).mean() > 0.99 and (i_scr == i_spl).mean() > 0.99
 
 
+@pytest.mark.parametrize('N,d,chunk', [(3000, 512, 2), (5000, 768, 3), (1500, 512, 1)])
+def test_dedup_screen_column_chunks_continue_the_candidate_lists(engine, N, d, chunk, monkeypatch):
+    """Large inputs run the screen as one launch per column chunk; a row's candidate lists travel from chunk to chunk through
+    `cand`.  Forced here on small inputs (VTF_SCREEN_CHUNK tiles per launch): the keys must be BIT-IDENTICAL to the
+    single-launch screen -- the same elements enter the same lists in the same order."""
+    K = engine.K
+    X = plant_dupes(blobs(N, d, kc=4, seed=9, normalize=(d == 512)), frac=20, seed=2, normalize=(d == 512))[0]
+    Xn = K.normalize_rows(dev(X))
+    monkeypatch.setenv('VTF_SCREEN_CHUNK', '100000')
+    one = K.cosine_dedup_tc(Xn, 0, 1, 0.2, mode='screen').cpu().numpy()
+    assert K.dedup_stats['screen_launches'] == 1
+    monkeypatch.setenv('VTF_SCREEN_CHUNK', str(chunk))
+    many = K.cosine_dedup_tc(Xn, 0, 1, 0.2, mode='screen').cpu().numpy()
+    units = (N + 255) // 256
+    assert K.dedup_stats['screen_launches'] == (units + chunk - 1) // chunk > 1
+    assert np.array_equal(one, many)
+    # and two ranks' shares (unit-cyclic) cover every row exactly as the single rank does
+    k0 = K.cosine_dedup_tc(Xn, 0, 2, 0.2, mode='screen').cpu().numpy()
+    k1 = K.cosine_dedup_tc(Xn, 1, 2, 0.2, mode='screen').cpu().numpy()
+    assert np.array_equal(np.minimum(k0.view(np.uint64), k1.view(np.uint64)), one.view(np.uint64))
+
+
 def test_dedup_screen_flags_rows_it_cannot_decide(engine):
     """The screen keeps the four best candidates per column half and evaluates them exactly; a row is undecidable only if its
     exact minimum is above the threshold while a FIFTH column of a half could still be below -- i.e. five or more earlier

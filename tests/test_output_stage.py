@@ -132,3 +132,23 @@ def test_device_resident_embeddings_go_through_the_drop_in_entry_points(tmp_path
     ih, _ = grouping.classify(Xh, R, [str(i) for i in range(7)], 0.8, False, None, None)
     idv, _ = grouping.classify(Xd, torch.from_numpy(R).cuda(), [str(i) for i in range(7)], 0.8, False, None, None)
     assert np.array_equal(ih, idv)
+
+
+@pytest.mark.gpu
+def test_pageable_upload_is_exact_and_used_for_plain_numpy_inputs(engine):
+    """main.py:71 hands the grouping stage an ordinary (pageable) numpy array; large ones go to the device through
+    vtf_upload_pageable (native threads + page-locked double buffers).  Byte-exact, any size, repeated calls reuse the buffers."""
+    import torch
+    K = engine.K
+    rng = np.random.default_rng(0)
+    for n_rows in (1, 4097, 40000):
+        A = rng.standard_normal((n_rows, 516), dtype=np.float32)          # 516 columns: pieces end in the middle of rows
+        for threads in (1, 3, 8):
+            got = K.upload_pageable(A, torch.float32, threads)
+            assert torch.equal(got.cpu(), torch.from_numpy(A))
+    big = rng.standard_normal((20000, 512), dtype=np.float32)             # 41 MB: engine.to_device takes the native path
+    t = engine.to_device(big)
+    assert t.is_cuda and torch.equal(t.cpu(), torch.from_numpy(big))
+    a = engine.dedup(big[:9000], 0.2)
+    b = engine.dedup(torch.from_numpy(big[:9000]).cuda(), 0.2)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -346,8 +346,8 @@ extern "C" {
 
 // column tiles per launch: the whole triangle when the operand fits in L2 with room to spare, else <= 48 MB of B per chunk
 static int64_t screen_chunk_tiles(int64_t n_units, int d) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("VTF_SCREEN_CHUNK"); forced = e ? atoi(e) : 0; }
+    const char* e = getenv("VTF_SCREEN_CHUNK");          // read per call: the tests force short chunks on small inputs
+    const int forced = e ? atoi(e) : 0;
     if (forced > 0) return min((int64_t)forced, n_units);
     const int64_t tile_bytes = 256ll * d * 2;
     if (n_units * tile_bytes <= (64ll << 20)) return n_units;

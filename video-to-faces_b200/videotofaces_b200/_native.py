@@ -67,6 +67,7 @@ SIGNATURES = {
     'vtf_dedup_pack': (c_int, [c_vp, c_i64, c_int, c_i64, c_f32, c_vp, c_vp, c_vp]),
     'vtf_cosine_dedup_tc': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_vp, c_vp]),
     'vtf_debug_sweep_timing': (c_int, [c_vp]),
+    'vtf_upload_pageable': (c_int, [c_vp, c_vp, c_sz, c_int, c_vp]),
     'vtf_dedup_screen_launches': (c_int, [c_i64, c_int]),
     'vtf_dedup_screen': (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'vtf_dedup_refine4': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),

@@ -85,6 +85,13 @@ class CudaKernels:
         nv.call('vtf_center_rows_stats', ptr(X), c_i64(N), c_int(d), ptr(mean32), ptr(out), None, ptr(stats), stream())
         return out, stats
 
+    def upload_pageable(self, A, dtype, threads, out=None):
+        """C-contiguous numpy array in pageable memory -> device tensor (native threads + page-locked double buffers)."""
+        t = out if out is not None else torch.empty(A.shape, dtype=dtype, device=self.device)
+        assert A.flags['C_CONTIGUOUS'] and t.is_contiguous() and t.numel() * t.element_size() == A.nbytes
+        nv.call('vtf_upload_pageable', nv.c_vp(A.ctypes.data), ptr(t), nv.c_sz(A.nbytes), c_int(threads), stream())
+        return t
+
     def gather_rows(self, X, idx):
         N, d = self._chk(X)
         out = self.empty((idx.numel(), d), torch.float32)
