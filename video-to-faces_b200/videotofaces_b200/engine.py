@@ -691,6 +691,8 @@ class GroupingEngine:
         active = (1 << nL) - 1
         n_iter, strict, counts_fin = [0] * nL, [False] * nL, [None] * nL
         log = dict(iters=0, fixed=[], listed=[])
+        kmax = max(ks)
+        valid = np.arange(kmax)[None, :] < np.asarray(ks)[:, None]              # [nL, kmax]: real cluster slots of a stats row
 
         def m_step(which, counts, changed):
             # cluster sizes / change counts of labels_new, labels_all = labels_new, and the sums brought up to date: from the
@@ -716,17 +718,22 @@ class GroupingEngine:
                 comm.allreduce_sum(cc)
             C_new, stats = K.wide_update(acc_g, inv_two_s, counts, changed, off, active, C_all, stride)
             st = stats.cpu().numpy()                                           # the one D2H of the iteration
-            for L in range(nL):
-                if not (active >> L) & 1:
-                    continue
+            # the per-labelling decisions for all labellings at once (31 of them, 227 iterations in config 4: a Python loop
+            # over every active labelling was 0.15 ms of GPU idle per iteration); only labellings where something happens
+            # -- an empty cluster, a stop -- are visited one by one
+            act = np.array([(active >> L) & 1 for L in range(nL)], dtype=bool)
+            empty = ((st[:, 2:2 + kmax] == 0) & valid).any(axis=1) & act
+            for L in np.nonzero(act)[0]:
+                n_iter[L] = it + 1
+            for L in np.nonzero(act & (empty | (st[:, 1] == 0) | (st[:, 0] <= ctx.tol)))[0]:
+                L = int(L)
                 lo, hi = int(off[L]), int(off[L + 1])
                 stL = st[L, :2 + hi - lo]
-                if (stL[2:] == 0).any():                                       # empty cluster: relocate (rare)
+                if empty[L]:                                                   # empty cluster: relocate (rare)
                     sums = acc_g[lo:hi].to(torch.float64) * inv_two_s
                     cn, _, stL = self._relocate_empty(ctx, labels_all[L], C_all[lo:hi].contiguous(), sums,
                                                       counts[lo:hi].contiguous(), changed[L:L + 1].contiguous(), stL)
                     C_new[lo:hi] = cn
-                n_iter[L] = it + 1
                 if stL[1] == 0:                                                # labels == labels_old, _kmeans.py:723
                     strict[L] = True
                     active &= ~(1 << L)
