@@ -159,6 +159,50 @@ class GroupingEngine:
         torch.cuda.current_stream().synchronize()
         return [v.numpy().copy() for v in views]
 
+    def to_host_async(self, tensors):
+        """to_host that does not wait: the copies are queued on a side stream behind what the current stream has been given so
+        far, and a helper thread waits for them and copies the results out of the page-locked staging buffer (numpy releases
+        the GIL for the copies) -- while the caller goes on launching work.  `.result()` joins the thread and returns the numpy
+        arrays.  Used for the labels and centres of a k-range, which are final before the silhouette sweep starts: their
+        trip to the host hides behind the sweep instead of following it."""
+        if self.device.type != 'cuda':
+            res = [t.detach().cpu().numpy() for t in tensors]
+            return type('Done', (), {'result': staticmethod(lambda: res)})()
+        import threading
+        sizes = [((t.numel() * t.element_size() + 255) // 256) * 256 for t in tensors]
+        total = sum(sizes)
+        if getattr(self, '_stage_async', None) is None or self._stage_async.numel() < total:
+            self._stage_async = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        if getattr(self, '_d2h_stream', None) is None:
+            self._d2h_stream = torch.cuda.Stream()
+        side = self._d2h_stream
+        side.wait_stream(torch.cuda.current_stream())
+        views, at = [], 0
+        with torch.cuda.stream(side):
+            for t, sz in zip(tensors, sizes):
+                v = self._stage_async[at:at + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+                src = t.contiguous()
+                src.record_stream(side)
+                v.copy_(src, non_blocking=True)
+                views.append(v)
+                at += sz
+            done = torch.cuda.Event()
+            done.record(side)
+        box = {}
+
+        def finish():
+            done.synchronize()
+            box['out'] = [v.numpy().copy() for v in views]
+        th = threading.Thread(target=finish, daemon=True)
+        th.start()
+
+        class _Pending:
+            @staticmethod
+            def result():
+                th.join()
+                return box['out']
+        return _Pending()
+
     def upload_replicated(self, A):
         """Host matrix -> the same full matrix on every rank.  With several ranks each one uploads only its row
         shard over its own PCIe link and the shards are all-gathered over NVLink (2 GB: ~3 ms at 8 GPUs) instead

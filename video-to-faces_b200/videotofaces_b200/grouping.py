@@ -81,9 +81,15 @@ def cluster_labels(X, clusters, rstate, inits=None, normalize=False):
     clusters = [c for c in clusters if c <= n]                                 # grouping.py:95
     with eng.solo_if(eng.too_small_to_shard(n)):
         ctx, results = eng.kmeans_sweep(X, clusters, rstate, inits=inits, normalize=normalize)      # grouping.py:99-101
-        scores = eng.cluster_scores(ctx, results)                              # grouping.py:104-108
+        # labels and centres are final here: their way to the host (side stream, helper thread) hides behind the sweep
+        pending = eng.to_host_async([r.labels for r in results] + [r.centers for r in results])
+        try:
+            scores = eng.cluster_scores(ctx, results)                          # grouping.py:104-108
+        except BaseException:
+            pending.result()                                                   # the staging buffer is free again
+            raise
     best_k = max(scores, key=lambda s: s[1])[0] if scores else None            # grouping.py:116 (first max)
-    host = eng.to_host([r.labels for r in results] + [r.centers for r in results])      # one D2H sync for all labels and centres
+    host = pending.result()
     nk = len(results)
     return dict(clusters=clusters, labels=host[:nk], scores=scores, best_k=best_k,
                 inertia=[r.inertia for r in results], n_iter=[r.n_iter for r in results],
