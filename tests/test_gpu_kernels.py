@@ -577,6 +577,22 @@ def test_dedup_screen_column_chunks_continue_the_candidate_lists(engine, N, d, c
     assert np.array_equal(np.minimum(k0.view(np.uint64), k1.view(np.uint64)), one.view(np.uint64))
 
 
+@pytest.mark.parametrize('N', [2, 3, 255, 256, 257, 513, 1024])
+def test_dedup_screen_on_tiny_and_ragged_inputs(engine, N):
+    """The tensor-core screen forced onto inputs of less than one or just over a whole number of 256-row units (padding rows
+    and columns, a single work item, items of one tile): same decisions and distances as the fp32 kernel."""
+    d = 512
+    X = blobs(max(N, 8), d, kc=2, seed=N)[:N].copy()
+    if N >= 3:
+        X[N - 1] = X[0]                                       # an exact duplicate of the first row in the last row
+    m_tc, i_tc, idx_tc = engine.dedup(X, 0.2, force='tc')
+    m_fp, i_fp, idx_fp = engine.dedup(X, 0.2, force='simt')
+    assert np.array_equal(idx_tc, idx_fp)
+    np.testing.assert_allclose(m_tc[1:], m_fp[1:], rtol=1e-5, atol=4e-7)
+    if N >= 3:
+        assert idx_tc.size >= 1 and idx_tc[-1] == N - 1 and i_tc[N - 1] == 0 and m_tc[N - 1] <= 1e-6
+
+
 def test_dedup_screen_flags_rows_it_cannot_decide(engine):
     """The screen keeps the four best candidates per column half and evaluates them exactly; a row is undecidable only if its
     exact minimum is above the threshold while a FIFTH column of a half could still be below -- i.e. five or more earlier

@@ -152,3 +152,26 @@ def test_pageable_upload_is_exact_and_used_for_plain_numpy_inputs(engine):
     a = engine.dedup(big[:9000], 0.2)
     b = engine.dedup(torch.from_numpy(big[:9000]).cuda(), 0.2)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.gpu
+def test_results_that_travel_behind_the_sweep_equal_the_synchronous_copy(engine):
+    """cluster_labels sends labels and centres to the host on a side stream while the sweep runs (engine.to_host_async); the
+    arrays equal a plain synchronous copy, and a second call reuses the staging buffer without mixing results up."""
+    import torch
+    from videotofaces_b200 import grouping
+    from videotofaces_b200.synth import blobs
+    ts = [torch.arange(100000, device='cuda', dtype=torch.int32) * 3, torch.randn(7, 512, device='cuda'),
+          torch.zeros(0, device='cuda', dtype=torch.int32)]
+    p1 = engine.to_host_async(ts)
+    a = p1.result()
+    p2 = engine.to_host_async([t + 1 for t in ts[:2]])
+    b = p2.result()
+    for got, t in zip(a, ts):
+        assert np.array_equal(got, t.cpu().numpy())
+    assert np.array_equal(b[0], (ts[0] + 1).cpu().numpy()) and np.array_equal(b[1], (ts[1] + 1).cpu().numpy())
+    X = blobs(9000, 512, kc=3, seed=4)
+    r1 = grouping.cluster_labels(X, [2, 3, 4], 0)
+    ctx, res = engine.kmeans_sweep(X, [2, 3, 4], 0)
+    assert all(np.array_equal(l, r.labels.cpu().numpy()) for l, r in zip(r1['labels'], res))
+    assert all(np.array_equal(c, r.centers.cpu().numpy()) for c, r in zip(r1['centers'], res))
