@@ -290,12 +290,24 @@ class GroupingEngine:
         with self.span('normalize'):
             Xn = self.K.normalize_rows(X)
         with self.span('dedup', flops=float(N) * N * d):
-            if use_tc:
+            key_h = None
+            if use_tc and not self.comm.active and getattr(self.K, 'dedup_defer', False):
+                # one rank: the screen's "units to re-sweep" count comes down WITH the keys (one synchronisation, not two)
+                key, n_flag, resweep = self.K.cosine_dedup_tc(Xn, 0, 1, float(np.float32(threshold)), defer=True)
+                if n_flag is None:
+                    key_h = self.to_host([key])[0]
+                else:
+                    key_h, nf = self.to_host([key, n_flag])
+                    if int(nf[0]) > 0:
+                        resweep()
+                        key_h = self.to_host([key])[0]
+            elif use_tc:
                 key = self.K.cosine_dedup_tc(Xn, self.comm.rank, self.comm.world, float(np.float32(threshold)))
             else:
                 key = self.K.cosine_dedup(Xn, self.comm.rank, self.comm.world)
-        self.comm.allreduce_min(key)
-        key_h = self.to_host([key])[0]
+        if key_h is None:
+            self.comm.allreduce_min(key)
+            key_h = self.to_host([key])[0]
         mins = (key_h >> 32).astype(np.uint32).view(np.float32)
         inds = (key_h & 0xffffffff).astype(np.int64)
         idx = (mins <= np.float32(threshold)).nonzero()[0]                    # dupes.py:65, fp32 compare

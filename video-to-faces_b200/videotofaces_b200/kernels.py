@@ -383,7 +383,9 @@ class CudaKernels:
 
     DEDUP_SCREEN_EPS = 1.0e-3          # bound of the single-MMA screen's error on a cosine similarity of unit rows
 
-    def cosine_dedup_tc(self, Xn, rank, world, thr=None, mode=None):
+    dedup_defer = True                 # cosine_dedup_tc(defer=True): the re-sweep decision is left to the caller
+
+    def cosine_dedup_tc(self, Xn, rank, world, thr=None, mode=None, defer=False):
         """Tensor-core dedup.  mode 'screen' (default when a threshold is given): single-MMA fp16 screen that keeps the best
         candidates per row + exact fp32 re-evaluation, with the units whose decision at `thr` the screen cannot guarantee
         re-swept by the split-fp16 kernel; mode 'split': split-fp16 operands (hi + lo), three MMAs per K step, everywhere.
@@ -403,7 +405,7 @@ class CudaKernels:
             nv.call('vtf_cosine_dedup_tc', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), c_int(rank), c_int(world),
                     ptr(key), stream())
             nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
-            return key
+            return (key, None, None) if defer else key
         cand = self.empty((N, 8, 2), torch.int32)
         flags = self.zeros((P // 256 + 1,), torch.int32)         # [units] flags + [1] count
         n_launch = int(nv.load().vtf_dedup_screen_launches(N, d))
@@ -414,13 +416,20 @@ class CudaKernels:
         nv.call('vtf_dedup_refine4', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(cand), c_f32(scale),
                 c_f32(float('nan') if thr is None else float(thr)), c_f32(self.DEDUP_SCREEN_EPS), ptr(key), ptr(flags),
                 nv.c_vp(flags.data_ptr() + 4 * (P // 256)), stream())
-        if thr is not None and int(flags[-1].item()) > 0:         # rare: rows with two neighbours in the band right above thr
+        def resweep():
+            # rare: rows with five neighbours of a column half in the band right above thr -- their units go through the split sweep
             units = torch.nonzero(flags[:-1]).flatten().to(torch.int32)
             units = torch.flip(units, [0]).contiguous()          # largest units first
             self.dedup_stats['reswept_units'] = int(units.numel())
             nv.call('vtf_cosine_dedup_tc_units', ptr(hi), ptr(lo), c_i64(N), c_i64(P), c_int(d), c_f32(scale), ptr(units),
                     c_i64(units.numel()), ptr(key), stream())
             nv.call('vtf_dedup_refine', ptr(Xn), c_i64(N), c_int(d), c_int(rank), c_int(world), ptr(key), stream())
+        if defer:
+            # the caller downloads `flags[-1]` together with the keys (one synchronisation instead of two) and calls resweep()
+            # -- then downloads the keys again -- only if it is non-zero
+            return key, flags[-1:], resweep
+        if thr is not None and int(flags[-1].item()) > 0:
+            resweep()
         return key
 
     def hash_dedup(self, bits, rank, world):
