@@ -312,10 +312,18 @@ __global__ void __launch_bounds__(256) dedup_refine4_kernel(const float* __restr
         float best = INFINITY;
         uint32_t best_col = 0u;
         float g_unseen = -INFINITY;
+        // Only candidates whose SCREEN value is within twice the screen's error of the best screen value can hold the exact
+        // maximum (|screen - exact| <= eps * s^2 each): the others are skipped -- typically 6 of the 8 gathers of a row.
+        float g_top = -INFINITY;
+        for (int c = 0; c < 8; ++c) {
+            const uint2 e = cand[(size_t)row * 8 + c];
+            if (e.y != 0xffffffffu) g_top = fmaxf(g_top, __uint_as_float(e.x));
+        }
+        const float g_keep = g_top - 2.f * eps / inv_s2;
         for (int c = 0; c < 8; ++c) {
             const uint2 e = cand[(size_t)row * 8 + c];
             if ((c & 3) == 3) g_unseen = fmaxf(g_unseen, __uint_as_float(e.x));     // a half's fourth best bounds everything it did not keep
-            if (e.y == 0xffffffffu) continue;
+            if (e.y == 0xffffffffu || __uint_as_float(e.x) < g_keep) continue;
             const float4* b = reinterpret_cast<const float4*>(Xn + (size_t)e.y * d);
             float s = 0.f;
             for (int v = lane; v < nvec; v += 32) {
