@@ -67,3 +67,20 @@ def test_sass_contains_blackwell_tensor_path():
     sass = subprocess.run(['cuobjdump', '-sass', _native.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM'):
         assert mnemonic in sass, mnemonic
+
+
+def test_dedup_screen_launch_plan_is_host_arithmetic(monkeypatch):
+    """vtf_dedup_screen_launches(N, d): column chunks (= launches = claim counters) of the dedup screen.  One launch while the
+    fp16 operand fits in L2 with room to spare (64 MB), else chunks of at most 48 MB; VTF_SCREEN_CHUNK overrides (tests)."""
+    from videotofaces_b200 import _native as nv
+    lib = nv.load()
+    monkeypatch.delenv('VTF_SCREEN_CHUNK', raising=False)
+    assert lib.vtf_dedup_screen_launches(0, 512) == 0 and lib.vtf_dedup_screen_launches(1, 512) == 0
+    assert lib.vtf_dedup_screen_launches(2, 512) == 1
+    assert lib.vtf_dedup_screen_launches(50_000, 512) == 1                 # config 2: 51 MB of operand
+    units = (200_000 + 255) // 256                                         # 205 MB: chunks of 48 MB / (256 * 512 * 2) = 192 tiles
+    assert lib.vtf_dedup_screen_launches(200_000, 512) == (units + 191) // 192
+    units = (4_000_000 + 255) // 256                                       # config 5: 128 tiles per chunk at d = 768
+    assert lib.vtf_dedup_screen_launches(4_000_000, 768) == (units + 127) // 128
+    monkeypatch.setenv('VTF_SCREEN_CHUNK', '2')
+    assert lib.vtf_dedup_screen_launches(3000, 512) == 6
